@@ -1,0 +1,265 @@
+/*
+ * ts_b200.h -- C ABI of the B200-native policy-update hot path for Tianshou-style RL.
+ *
+ * The reference (thu-ml/tianshou 2.0.1) has NO FFI: its hot path is Python + numba @njit +
+ * stock torch ops.  This header declares the entry points a maintainer binds (ctypes / cffi,
+ * see INTEGRATION.md) in place of those numba kernels and torch loops.  Every function
+ *   - takes plain device pointers, sizes and a cudaStream_t (passed as void*),
+ *   - is asynchronous on that stream (no host sync, no allocation, no hidden global state),
+ *   - returns 0 on success, non-zero on error; ts_last_error() gives the thread-local message.
+ * Pointers are DEVICE pointers unless a parameter is documented as "host".  "u8" flags are
+ * numpy/torch bool storage (one byte, 0/1).
+ *
+ * Each declaration cites the reference code it replaces (path:line under /root/reference).
+ */
+#ifndef TS_B200_H_
+#define TS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TS_B200_ABI_VERSION 1
+
+typedef void* ts_stream_t; /* cudaStream_t */
+
+/* dtype tags for the few polymorphic entry points */
+enum { TS_F32 = 0, TS_F64 = 1 };
+
+int ts_version(void);
+const char* ts_last_error(void);
+/* number of kernel launches issued through this library by the calling process (for bench.py's
+ * "gpu_launches" claim); ts_reset_launch_count() zeroes it. */
+int64_t ts_launch_count(void);
+void ts_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) GAE: segmented reverse scan.
+ * Replaces numba `_gae` (tianshou/algorithm/algorithm_base.py:1085-1140) together with the
+ * value-mask / end-flag / return-scaling arithmetic around it in
+ * `Algorithm.compute_episodic_return` (:704-719) and
+ * `ActorCriticOnPolicyAlgorithm._add_returns_and_advantages` (modelfree/a2c.py:131-152):
+ *
+ *   s      = rms_state ? sqrt(rms_state.var + rms_eps) : 1         (return_scaling un-normalise)
+ *   vs     = v_s[i] * s ;  vn = v_s_next[i] * s * (terminated ? !terminated[i] : 1)
+ *   delta  = rew[i] + vn*gamma - vs
+ *   end    = (truncated?truncated[i]:0) | (terminated_ends?terminated[i]:0) | (extra_end?extra_end[i]:0)
+ *   adv[i] = delta + (1-end)*gamma*lam * adv[i+1]        (adv[n] = 0; f64 accumulate)
+ *   ret[i] = (adv[i] + vs) / s
+ * and, if rms_state != NULL, merges mean/var/count of the UN-scaled returns (adv+vs) into
+ * rms_state with Chan's formula exactly as `RunningMeanStd.update`
+ * (tianshou/utils/statistics.py:99-114) -- after every block has read the old var.
+ *
+ * v_s / v_s_next: n values of v_dtype (TS_F32|TS_F64).  rew: n f64 (the buffer stores float64,
+ * data/buffer/manager.py:183).  terminated / truncated / extra_end: n u8, each nullable.
+ * terminated_ends: if non-zero `terminated` also ends a segment (the normal case); the value
+ * mask always uses it when non-NULL.  adv_out / ret_out: n values of out_dtype.
+ * rms_state: device double[3] = {mean, var, count} (nullable).
+ * workspace: device scratch of ts_gae_workspace_bytes(n) bytes (contents ignored).
+ * ------------------------------------------------------------------------------------------ */
+size_t ts_gae_workspace_bytes(int64_t n);
+int ts_gae(const void* v_s, const void* v_s_next, int v_dtype, const double* rew,
+           const uint8_t* terminated, const uint8_t* truncated, const uint8_t* extra_end,
+           int terminated_ends, int64_t n, double gamma, double lam, double* rms_state,
+           double rms_eps, void* adv_out, void* ret_out, int out_dtype, void* workspace,
+           ts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) n-step return: windowed gather-reduce.
+ * Replaces numba `_nstep_return` (algorithm_base.py:1160-1222) and the whole-buffer
+ * `end_flag_B = done.copy(); end_flag_B[unfinished] = True` preparation (:799-800).
+ *   rew: B f64 (whole buffer), end_flag: B u8, target_q: I*A f32 (already value-masked),
+ *   stacked_idx: n_step rows of I int64 (row k = next^k(indices)), out: I*A of out_dtype.
+ * Arithmetic is f64 in the reference's operation order (no FMA contraction) => bit-exact f64.
+ * ------------------------------------------------------------------------------------------ */
+int ts_nstep_return(const double* rew, const uint8_t* end_flag, const float* target_q,
+                    const int64_t* stacked_idx, int64_t I, int64_t A, int32_t n_step,
+                    double gamma, void* out, int out_dtype, ts_stream_t stream);
+
+/* end_flag[i] = done[i] | (i is the last written slot of a non-empty sub-buffer); B = offset[E].
+ * Replaces algorithm_base.py:799-800 + manager.py:85-91 without the host copy. */
+int ts_buffer_end_flags(const uint8_t* done, const int64_t* offset, const int64_t* last_index,
+                        const int64_t* lengths, int64_t E, uint8_t* end_flag_out,
+                        ts_stream_t stream);
+
+/* target_q[i, :] *= !terminated[idx[i]]  (Algorithm.value_mask, algorithm_base.py:633-651,798) */
+int ts_value_mask_rows(float* target_q, const uint8_t* terminated, const int64_t* idx, int64_t I,
+                       int64_t A, ts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Replay-buffer index kernels (bit-exact int64).
+ * Sub-buffer e owns slots [offset[e], offset[e+1]); lengths[e] = current size; last_index[e] =
+ * absolute last-written slot.  A plain ReplayBuffer is the E=1 case.
+ * Replace numba `_next_index` / `_prev_index` (tianshou/data/buffer/manager.py:339-363,
+ * :311-336) and ReplayBuffer.next/prev (buffer_base.py:319-334).
+ * ------------------------------------------------------------------------------------------ */
+int ts_next_index(const int64_t* index, int64_t n, const int64_t* offset, int64_t E,
+                  const uint8_t* done, const int64_t* last_index, const int64_t* lengths,
+                  int64_t* out, ts_stream_t stream);
+int ts_prev_index(const int64_t* index, int64_t n, const int64_t* offset, int64_t E,
+                  const uint8_t* done, const int64_t* last_index, const int64_t* lengths,
+                  int64_t* out, ts_stream_t stream);
+/* out[k*n + i] = next^k(index[i]) for k = 0..n_step-1 (algorithm_base.py:775-779). */
+int ts_stack_next_indices(const int64_t* index, int64_t n, int32_t n_step, const int64_t* offset,
+                          int64_t E, const uint8_t* done, const int64_t* last_index,
+                          const int64_t* lengths, int64_t* out, ts_stream_t stream);
+/* ReplayBufferManager.unfinished_index (manager.py:85-91; buffer_base.py:314-317): ordered list
+ * of last-written slots whose `done` is false.  out: capacity E; count_out: device int64[1]. */
+int ts_unfinished_index(const int64_t* offset, int64_t E, const uint8_t* done,
+                        const int64_t* last_index, const int64_t* lengths, int64_t* out,
+                        int64_t* count_out, ts_stream_t stream);
+/* sample_indices(0): all valid slots, sub-buffer-major, chronological inside each sub-buffer
+ * (manager.py:217-234, buffer_base.py:519-525).  seg_start: device int64[E+1] scratch that
+ * receives the exclusive prefix sum of lengths; out capacity >= sum(lengths); total_out int64[1]. */
+int ts_sample_all_indices(const int64_t* offset, int64_t E, const int64_t* last_index,
+                          const int64_t* lengths, int64_t* seg_start, int64_t* out,
+                          int64_t out_capacity, int64_t* total_out, ts_stream_t stream);
+/* mark[p] = 1 if idx[p] is in `members` (np.isin, algorithm_base.py:715).  table: device u8
+ * scratch of table_size >= max slot + 1, left zeroed on return. */
+int ts_mark_members(const int64_t* idx, int64_t n, const int64_t* members,
+                    const int64_t* member_count /* device int64[1] */, int64_t member_capacity,
+                    uint8_t* table, int64_t table_size, uint8_t* mark_out, ts_stream_t stream);
+/* dst[p, :] = src[idx[p], :] for rows of row_bytes (multiple of 4) -- ReplayBuffer.__getitem__
+ * (buffer_base.py:605-649) / Batch.__getitem__ (data/batch.py:714-738) for array leaves. */
+int ts_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t n, void* dst,
+                   ts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) Sum tree for prioritized replay (f64 tree, bit-exact indices).
+ * tree: double[2*bound], root at 1, leaves at [bound, bound+size) (data/utils/segtree.py:19-26).
+ * Replace numba `_setitem` (:95-101), `_reduce` (:104-116), `_get_prefix_sum_idx` (:119-134).
+ * ------------------------------------------------------------------------------------------ */
+/* tree[bound+index[k]] = value[k] (duplicates: last wins), then parents re-summed bottom-up. */
+int ts_segtree_setitem(double* tree, int64_t bound, const int64_t* index, const void* value,
+                       int value_dtype, int64_t n, ts_stream_t stream);
+/* out[0] = sum(leaves[start:end]) using the reference's bottom-up walk (same addition order). */
+int ts_segtree_reduce(const double* tree, int64_t bound, int64_t start, int64_t end, double* out,
+                      ts_stream_t stream);
+/* out[k] = min i such that value[k] <= sum(leaves[0..i]) (ties go left).  value: n f64. */
+int ts_segtree_prefix_sum_idx(const double* tree, int64_t bound, const double* value, int64_t n,
+                              int64_t* out, ts_stream_t stream);
+/* value[k] = u[k] * tree[1] then descent -- fuses `np.random.rand(bs) * weight.reduce()`
+ * (data/buffer/prio.py:65-66); u stays a host-drawn numpy stream uploaded by the caller. */
+int ts_segtree_sample(const double* tree, int64_t bound, const double* u, int64_t n, int64_t* out,
+                      ts_stream_t stream);
+/* PrioritizedReplayBuffer.update_weight (prio.py:81-90): w = |td|+eps; tree[idx] = w^alpha;
+ * prio_minmax (device double[2] = {max_prio, min_prio}) updated with max/min of w. */
+int ts_prio_update_weight(double* tree, int64_t bound, const int64_t* index, const void* td,
+                          int td_dtype, int64_t n, double alpha, double eps, double* prio_minmax,
+                          ts_stream_t stream);
+/* PrioritizedReplayBuffer.get_weight (+ batch-max normalisation, prio.py:69-79,104-106):
+ * out[k] = (tree[bound+idx[k]] / min_prio)^(-beta), divided by the batch max if weight_norm. */
+int ts_prio_get_weight(const double* tree, int64_t bound, const int64_t* index, int64_t n,
+                       const double* prio_minmax, double beta, int weight_norm, double* out,
+                       ts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) Actor-critic MLP (two tanh hidden layers of width `hidden`, separate actor and critic
+ * trunks, Gaussian policy head with state-independent log-sigma) -- the network of
+ * examples/mujoco/mujoco_ppo.py:90-120 built from tianshou/utils/net/common.py:172-179,343-369
+ * and continuous.py:144-169,220-238.
+ * All parameters live in ONE flat f32 buffer in torch layout ([out][in] row-major weights);
+ * offsets are in floats.  The same offsets index the flat gradient / Adam-moment buffers.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ts_actor_critic_desc {
+    int32_t obs_dim;  /* <= 64 */
+    int32_t act_dim;  /* <= 16 */
+    int32_t hidden;   /* 64 */
+    int32_t reserved;
+    int64_t a_w1, a_b1, a_w2, a_b2, a_w3, a_b3, a_logstd; /* actor: W1[h][obs] .. W3[act][h], logstd[act] */
+    int64_t c_w1, c_b1, c_w2, c_b2, c_w3, c_b3;           /* critic: .. W3[1][h], b3[1] */
+    int64_t n_params;
+} ts_actor_critic_desc;
+
+/* v_out[r] = critic(obs[r, :]) for r < n.  Up to two (obs, out) pairs in one launch (v_s and
+ * v_s_ of a2c.py:123-126); pass obs1 = NULL for a single pass.  obs rows are obs_dim f32, dense. */
+int ts_critic_forward(const float* params, const ts_actor_critic_desc* desc /* host */,
+                      const float* obs0, float* v_out0, const float* obs1, float* v_out1,
+                      int64_t n, ts_stream_t stream);
+/* logp_out[r] = Independent(Normal(mu(obs[r]), exp(logstd)), 1).log_prob(act[r])
+ * (ppo.py:157-161 with reinforce.py:167-192).  mu_out (n*act_dim, nullable) receives mu. */
+int ts_actor_logp(const float* params, const ts_actor_critic_desc* desc /* host */,
+                  const float* obs, const float* act, int64_t n, float* logp_out, float* mu_out,
+                  ts_stream_t stream);
+
+typedef struct ts_ppo_hparams {
+    /* all hyper-parameters are doubles (Python floats in the reference); the kernels narrow to
+     * f32 at the point where torch would (scalar operand of an f32 tensor op) */
+    double eps_clip;
+    double dual_clip;     /* <= 0: disabled */
+    double vf_coef;
+    double ent_coef;
+    double max_grad_norm; /* <= 0: no clipping */
+    double adv_eps;       /* 1e-8 in the reference (self._eps) */
+    /* Adam (torch.optim.Adam semantics, algorithm/optim.py:89-110) */
+    double lr, beta1, beta2, adam_eps, weight_decay;
+    int32_t value_clip;
+    int32_t advantage_normalization;
+} ts_ppo_hparams;
+
+/* Per-optimiser-step device statistics: {loss, clip_loss, vf_loss, ent_loss, grad_norm, n_rows,
+ * 0, 0} -- 8 floats per step (ppo.py:213-216 without the 4 host syncs). */
+#define TS_PPO_STATS_STRIDE 8
+/* grad buffer layout: n_params floats + TS_PPO_GRAD_EXTRA scalar slots {sum_clip, sum_vf,
+ * sum_ent, n_rows} so that ONE allreduce carries gradients and loss sums. */
+#define TS_PPO_GRAD_EXTRA 4
+
+/* One minibatch forward/backward (ppo.py:179-211 + loss.backward of algorithm_base.py:497):
+ * rows are perm[lo..hi) of the rollout tensors; ACCUMULATES d(loss)/d(params) * (local_rows /
+ * global_rows weighting is the caller's: gradients are sums scaled by 1/global_rows) into grad
+ * and the loss sums into grad[n_params..].  `global_rows` is the minibatch size over all ranks
+ * (the mean's denominator); adv_moments: device float[2] = {mean, std} when
+ * advantage_normalization, else NULL.  perm may be NULL (identity). */
+int ts_ppo_grad(const float* params, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
+                const float* obs, const float* act, const float* adv, const float* ret,
+                const float* logp_old, const float* v_s, const int32_t* perm, int64_t lo,
+                int64_t hi, int64_t global_rows, const float* adv_moments, float* grad,
+                ts_stream_t stream);
+/* mean and unbiased std of adv[perm[lo..hi)] (ppo.py:184-186) -> out[0..1]; partial sums go to
+ * sums (device double[2]) first so a multi-GPU caller can allreduce them; pass finalize=1 to
+ * turn (sum, sumsq, count=global_rows) into {mean, std}. */
+int ts_minibatch_adv_sums(const float* adv, const int32_t* perm, int64_t lo, int64_t hi,
+                          double* sums, ts_stream_t stream);
+int ts_adv_moments_finalize(const double* sums, int64_t global_rows, float* out,
+                            ts_stream_t stream);
+/* clip_grad_norm_ + Adam.step + zero_grad (algorithm_base.py:496-500; torch/optim/adam.py
+ * single-tensor path) on the flat buffers, and one row of per-step statistics.
+ * step_count: device int64[1], incremented.  stats_row: device float[TS_PPO_STATS_STRIDE]. */
+int ts_clip_adam_step(float* params, float* grad, float* exp_avg, float* exp_avg_sq,
+                      int64_t* step_count, const ts_actor_critic_desc* desc,
+                      const ts_ppo_hparams* hp, float* stats_row, ts_stream_t stream);
+
+/* The whole single-GPU `PPO._update_with_batch` loop (ppo.py:164-224) on one stream:
+ * for r in repeat: [recompute v_s/returns/adv (a2c.py:115-153)] ; for each minibatch of
+ * perm[r] (Batch.split bounds, batch.py:1199-1215): grad + clip + Adam.  No host sync.
+ * perm: repeat*N int32 (row r = the permutation of repeat r).  bounds: host int64[2*n_mb].
+ * rollout tensors (all N rows, device): obs, obs_next, act f32; rew f64; terminated,
+ * truncated, extra_end u8; v_s, returns, adv, logp_old f32 (in/out: must be valid on entry,
+ * rewritten when recompute_adv).  stats: repeat*n_mb rows.  rms_state as in ts_gae (nullable
+ * when return_scaling is off).  v_next_tmp: N f32 scratch.  gae_ws: ts_gae_workspace_bytes(N).
+ * grad: n_params + TS_PPO_GRAD_EXTRA floats, zero on entry. adv_tmp: double[2]+float[2] bytes.
+ */
+int ts_ppo_update(float* params, float* grad, float* exp_avg, float* exp_avg_sq,
+                  int64_t* step_count, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
+                  const float* obs, const float* obs_next, const float* act, const double* rew,
+                  const uint8_t* terminated, const uint8_t* truncated, const uint8_t* extra_end,
+                  float* v_s, float* returns, float* adv, const float* logp_old,
+                  float* v_next_tmp, int64_t N, const int32_t* perm, int32_t repeat,
+                  const int64_t* bounds /* host */, int32_t n_minibatch, int32_t recompute_adv,
+                  double gamma, double lam, double* rms_state, double rms_eps, void* gae_ws,
+                  void* adv_tmp, float* stats, ts_stream_t stream);
+
+/* Device-side minibatch order (opt-in alternative to np.random.permutation, batch.py:1209):
+ * out[r*n + i] = pi_r(i), pi_r a keyed bijection of [0,n) (cycle-walking Feistel/Philox). */
+int ts_make_permutation(uint64_t seed, int32_t first_epoch, int32_t n_epochs, int64_t n,
+                        int32_t* out, ts_stream_t stream);
+/* int64 -> int32 narrowing of a host-drawn permutation already uploaded to the device. */
+int ts_narrow_i64_i32(const int64_t* src, int64_t n, int32_t* dst, ts_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TS_B200_H_ */
