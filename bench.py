@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- transitions/sec through PPO ``Algorithm.update()`` (v1: ``learn()``), obs=17.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): synthetic HalfCheetah-shaped rollout of
+4096 envs x 128 steps per GPU (N = 524,288 transitions, obs 17, act 6), actor/critic MLP[64,64]
+tanh, hyper-parameters of examples/mujoco/mujoco_ppo.py (gamma .99, lambda .95, eps .2, vf .25,
+ent 0, max_grad_norm .5, value_clip, recompute_advantage, return_scaling, Adam 3e-4),
+minibatch 16384, repeat 10  ->  320 optimiser steps + 10 value/GAE passes per update.
+A "step" of this benchmark is ONE ``update(buffer, batch_size=16384, repeat=10)`` call.
+
+Reported (one JSON line on rank 0):
+  value : transitions/s with the rollout already resident in HBM (device preprocess + update).
+  e2e   : transitions/s through the public API ``PPO.update(buffer, ...)`` with the rollout in
+          (pinned) host buffers: bulk H2D of the rollout and D2H of the loss table inside the
+          timed region.
+  roofline : dominant kernel (minibatch forward/backward) against the measured bf16 GEMM peak,
+             algorithmic flops 60,544 / row.
+  cpu_baseline / --impl reference : the numpy port of the reference's update (oracle/) timed on
+             this box's host cores on a bounded sample of the same workload.
+Multi-GPU (torchrun): weak scaling -- every rank owns its own 4096x128 rollout shard, the global
+minibatch is N x 16384 rows and ONE NCCL all-reduce of (gradient, loss sums) precedes each Adam
+step; value = all ranks' transitions / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OBS, ACT = 17, 6
+E_FULL, T_FULL = 4096, 128
+BATCH_SIZE, REPEAT = 16384, 10
+FLOP_TRAIN_PER_ROW = 60_544          # fwd+bwd of actor and critic
+FLOP_PER_TRANSITION = REPEAT * 81_536 + 11_136
+METRIC = "transitions/sec through Algorithm.learn() (PPO, obs=17)"
+
+
+def load_peaks() -> tuple[dict, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows: list[list[str]] = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_host_buffer(E: int, T: int, seed: int, device):
+    from tianshou_b200.data import VectorReplayBuffer
+    from tianshou_b200.synthetic import fill_vector_buffer
+    buf = VectorReplayBuffer(E * T, E, device=device)
+    fill_vector_buffer(buf, np.random.default_rng(seed), E, T, OBS, ACT)
+    return buf
+
+
+# ------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_run(E: int, T: int, steps: int, warmup: int) -> dict:
+    """numpy port of the reference's PPO update (oracle/oracle_np.py) on E x T transitions,
+    same minibatch size / repeat / hyper-parameters; all host threads numpy's BLAS will use."""
+    from oracle import oracle_np as onp
+    from tianshou_b200.synthetic import synth_rollout
+    rng = np.random.default_rng(0)
+    cols: dict[str, list] = {k: [] for k in ("obs", "act", "rew", "terminated", "truncated", "obs_next")}
+    for s in synth_rollout(rng, E, T, OBS, ACT):
+        for k in cols:
+            cols[k].append(s[k])
+    # env-major flat order, like VectorReplayBuffer.sample(0)
+    roll = {k: np.stack(v, axis=1).reshape(E * T, *v[0].shape[1:]) for k, v in cols.items()}
+    N = E * T
+    unf = np.zeros(N, dtype=bool)
+    lastpos = np.arange(E) * T + T - 1
+    unf[lastpos] = ~(roll["terminated"][lastpos] | roll["truncated"][lastpos])
+    roll["unfinished"] = unf
+    g = np.random.default_rng(1)
+    def ortho(o, i, gain):
+        a = g.standard_normal((o, i)); q, _ = np.linalg.qr(a.T if o < i else a); q = q.T if o < i else q
+        return (gain * q[:o, :i]).astype(np.float32)
+    p = {"a_w1": ortho(64, OBS, 2 ** .5), "a_b1": np.zeros(64, np.float32), "a_w2": ortho(64, 64, 2 ** .5),
+         "a_b2": np.zeros(64, np.float32), "a_w3": 0.01 * ortho(ACT, 64, 2 ** .5), "a_b3": np.zeros(ACT, np.float32),
+         "a_logstd": np.full((ACT, 1), -0.5, np.float32), "c_w1": ortho(64, OBS, 2 ** .5), "c_b1": np.zeros(64, np.float32),
+         "c_w2": ortho(64, 64, 2 ** .5), "c_b2": np.zeros(64, np.float32), "c_w3": ortho(1, 64, 2 ** .5),
+         "c_b3": np.zeros(1, np.float32)}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(x) for k, x in p.items()}
+    hp = dict(eps_clip=0.2, dual_clip=None, vf_coef=0.25, ent_coef=0.0, max_grad_norm=0.5, adv_eps=1e-8, value_clip=True,
+              advantage_normalization=False, lr=3e-4, beta1=0.9, beta2=0.999, adam_eps=1e-8, weight_decay=0.0)
+    rms = onp.RunningMeanStd()
+    step = 0
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        perms = [np.random.permutation(N) for _ in range(REPEAT)]
+        res = onp.ppo_update(p, m, v, step, roll, perms, min(BATCH_SIZE, N), REPEAT, hp, rms, 0.99, 0.95, True)
+        step = res["step"]
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean_t = sum(times) / len(times)
+    try:
+        import threadpoolctl
+        cores = max([i.get("num_threads", 1) for i in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    return {"value": N / mean_t, "unit": "transitions/s", "cores": int(cores), "kind": "port",
+            "sample": f"{E} envs x {T} steps = {N} transitions, minibatch {min(BATCH_SIZE, N)}, repeat {REPEAT}, "
+                      f"{len(times)} timed update() calls of the numpy port (oracle/oracle_np.py)",
+            "ms_per_step": mean_t * 1e3}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    E = int(os.environ.get("TS_BENCH_CPU_ENVS", "256"))
+    res = cpu_reference_run(E, T_FULL, max(1, args.steps), max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "transitions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus) | {"cpu_sample": res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": f"PPO update(): synthetic HalfCheetah rollout {E_FULL} envs x {T_FULL} steps per GPU "
+                        f"(obs {OBS}, act {ACT}), MLP[64,64] tanh actor+critic, minibatch {BATCH_SIZE} per GPU, "
+                        f"repeat {REPEAT}, recompute_advantage, value_clip, return_scaling (BASELINE configs[1])",
+            "transitions_per_gpu": E_FULL * T_FULL, "global_minibatch": BATCH_SIZE * n_gpus, "repeat": REPEAT,
+            "parallelism": f"dp{n_gpus}", "l2": "explicit 256 MiB L2 flush between timed update() calls",
+            "minibatch_shuffle": "device (ts_make_permutation); the reference-RNG-exact 'numpy' mode is reported "
+                                 "as e2e_numpy_rng"}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=E_FULL)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from tianshou_b200 import _cabi
+    from tianshou_b200._cabi import call, ptr, stream_ptr
+    from tianshou_b200.synthetic import build_mujoco_ppo
+    from tianshou_b200.utils import policy_within_training_step
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun)"
+    _cabi.load_library()
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    E, T = args.envs, T_FULL
+    N = E * T
+
+    buf = build_host_buffer(E, T, seed=rank, device=dev)
+    algo, actor, critic = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="device")
+    algo_np, _, _ = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="numpy")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters: int) -> float:
+        """sum of per-iteration device times (ms), L2 flushed before every iteration; max over ranks."""
+        evs = []
+        barrier()
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        barrier()
+        tot = sum(s.elapsed_time(e) for s, e in evs)
+        if world > 1:
+            t = torch.tensor([tot], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = float(t.item())
+        return tot
+
+    # ---- device-resident leg ("value"): rollout already in HBM ---------------------------------
+    with policy_within_training_step(algo.policy):
+        dev_batch, dev_idx = algo._sample(buf, 0)
+
+        def device_step():
+            b = algo._preprocess_batch(dev_batch, buf, dev_idx)
+            algo._update_with_batch(b, BATCH_SIZE, REPEAT)
+
+        def e2e_step():
+            algo.update(buffer=buf, batch_size=BATCH_SIZE, repeat=REPEAT)
+
+        def e2e_numpy_step():
+            algo_np.policy.is_within_training_step = True
+            algo_np.update(buffer=buf, batch_size=BATCH_SIZE, repeat=REPEAT)
+
+        for _ in range(W):
+            device_step()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        _cabi.reset_launch_count()
+        ms_dev = timed(device_step, K)
+        launches = _cabi.launch_count()
+        for _ in range(W):
+            e2e_step()
+        ms_e2e = timed(e2e_step, K)
+        clocks = sampler.stop() if rank == 0 else {}
+        e2e_numpy_step()
+        ms_np = timed(e2e_numpy_step, max(1, min(K, 2)))
+        n_np = max(1, min(K, 2))
+
+    # ---- roofline of the dominant kernel: events around isolated launches on its stream -------
+    hp = algo._ppo_hparams()
+    f = algo._flat
+    b = dev_batch
+    perm = torch.randperm(N, device=dev).to(torch.int32)
+    reps = 40
+    rows = min(BATCH_SIZE, N)
+    grad_events = []
+    for i in range(reps + 5):
+        lo = (i * rows) % max(1, N - rows + 1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        call("ts_ppo_grad", ptr(f.flat), C.byref(algo._desc), C.byref(hp), ptr(b.obs), ptr(b.act), ptr(b.adv),
+             ptr(b.returns), ptr(b.logp_old), ptr(b.v_s), ptr(perm), lo, lo + rows, rows, None, ptr(f.grad),
+             stream_ptr(dev))
+        e.record()
+        if i >= 5:
+            grad_events.append((s, e))
+    torch.cuda.synchronize()
+    f.grad.zero_()
+    grad_ms = sum(s.elapsed_time(e) for s, e in grad_events) / len(grad_events)
+    # GAE scan alone (HBM-bound kernel)
+    from tianshou_b200 import ops
+    gae_events = []
+    for i in range(25):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.gae(b.v_s, algo._buf("v_next", N, torch.float32), b.rew, b.terminated, b.truncated, b.get("_unfinished"),
+                gamma=0.99, gae_lambda=0.95, out=(b.adv, b.returns), workspace=algo._gae_workspace(N))
+        e.record()
+        if i >= 5:
+            gae_events.append((s, e))
+    torch.cuda.synchronize()
+    gae_ms = sum(s.elapsed_time(e) for s, e in gae_events) / len(gae_events)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    total_transitions = N * world
+    value = total_transitions * K / (ms_dev / 1e3)
+    e2e_value = total_transitions * K / (ms_e2e / 1e3)
+    e2e_np_value = total_transitions * n_np / (ms_np / 1e3)
+    meta_bytes = buf._extend_offset.nbytes + buf.last_index.nbytes + buf._sizes.nbytes
+    h2d = sum(np.asarray(buf._meta[k]).nbytes for k in ("obs", "obs_next", "act", "rew", "terminated", "truncated", "done")) + meta_bytes
+    n_mb = len(range(0, N, BATCH_SIZE))
+    d2h = REPEAT * n_mb * 8 * 4 + 3 * 8
+    grad_flops = FLOP_TRAIN_PER_ROW * rows
+    grad_tflops = grad_flops / (grad_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("ppo_grad_kernel_dram_bytes_per_launch")
+    gae_bytes = 27 * N
+    line = {
+        "metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (MLP fwd/bwd, Adam), f64 (GAE scan, running return statistics)", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / K},
+        "e2e_numpy_rng": {"value": e2e_np_value, "unit": "transitions/s", "ms_per_step": ms_np / n_np,
+                          "note": "public API with minibatch_shuffle='numpy': np.random.permutation per repeat on the host "
+                                  "(bit-identical minibatch composition to the reference)"},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "ppo_grad_kernel (fused minibatch fwd/bwd, fp32 SIMT)", "bound": "tensor",
+                     "achieved": grad_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": grad_tflops / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_flops_per_launch": grad_flops, "launch_ms": grad_ms, "rows_per_launch": rows},
+        "roofline_gae": {"kernel": "gae_scan_kernel", "bound": "hbm", "achieved": gae_bytes / (gae_ms * 1e-3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gae_bytes / (gae_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "algorithmic_bytes_per_launch": gae_bytes, "launch_ms": gae_ms, "peak_source": peak_src},
+        "flops_per_transition": FLOP_PER_TRANSITION,
+        "update_tflops": FLOP_PER_TRANSITION * total_transitions * K / (ms_dev / 1e3) / 1e12,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_run(int(os.environ.get("TS_BENCH_CPU_ENVS", "128")), T_FULL, 1, 1)
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

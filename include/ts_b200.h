@@ -58,14 +58,21 @@ void ts_reset_launch_count(void);
  * terminated_ends: if non-zero `terminated` also ends a segment (the normal case); the value
  * mask always uses it when non-NULL.  adv_out / ret_out: n values of out_dtype.
  * rms_state: device double[3] = {mean, var, count} (nullable).
+ * batch_moments_out: see ts_rms_merge below (nullable).
  * workspace: device scratch of ts_gae_workspace_bytes(n) bytes (contents ignored).
  * ------------------------------------------------------------------------------------------ */
 size_t ts_gae_workspace_bytes(int64_t n);
 int ts_gae(const void* v_s, const void* v_s_next, int v_dtype, const double* rew,
            const uint8_t* terminated, const uint8_t* truncated, const uint8_t* extra_end,
            int terminated_ends, int64_t n, double gamma, double lam, double* rms_state,
-           double rms_eps, void* adv_out, void* ret_out, int out_dtype, void* workspace,
-           ts_stream_t stream);
+           double rms_eps, double* batch_moments_out, void* adv_out, void* ret_out, int out_dtype,
+           void* workspace, ts_stream_t stream);
+/* Multi-GPU return scaling: when batch_moments_out (device double[3] = {count, mean, M2} of this
+ * call's un-scaled returns) is non-NULL, ts_gae writes it and leaves rms_state untouched; the
+ * caller all-gathers the triples and folds them in rank order with ts_rms_merge so that every
+ * replica holds the same RunningMeanStd. */
+int ts_rms_merge(double* rms_state, const double* moments /* parts x 3 */, int32_t parts,
+                 ts_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * (2) n-step return: windowed gather-reduce.

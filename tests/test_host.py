@@ -1,0 +1,163 @@
+"""CPU-side tests: Batch semantics, buffer bookkeeping + host RNG streams, C-ABI surface.
+(No kernel is executed here -- there is no CPU implementation of the device path.)"""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tianshou_b200.data import Batch, ReplayBuffer, VectorReplayBuffer
+from tianshou_b200.data.batch import minibatch_bounds
+from ts_testutil import ROOT, load_golden, set_buffer_state, synth_rollout
+
+
+# ------------------------------------------------------------------------------------- Batch
+def test_batch_basic_indexing_and_assignment():
+    b = Batch(a=np.arange(6).reshape(3, 2), b=Batch(c=np.zeros(3), d=torch.ones(3, 2)), e=None)
+    assert len(b) == 3 and Batch(a=np.zeros((3, 2)), c=np.zeros(3)).shape == [3]
+    s = b[[0, 2]]
+    assert s.a.tolist() == [[0, 1], [4, 5]] and s.b.d.shape == (2, 2) and s.e is None
+    b[1] = Batch(a=np.array([7, 7]), b=Batch(c=np.float64(5), d=torch.zeros(2)))
+    assert b.a[1].tolist() == [7, 7] and b.b.c[1] == 5
+    with pytest.raises(ValueError):
+        b[0] = Batch(zzz=1)
+    with pytest.raises(IndexError):
+        Batch()[0]
+    assert "a" in b and b.get("nope", 3) == 3
+    b2 = pickle.loads(pickle.dumps(b))
+    assert b2 == b
+
+
+def test_batch_cat_stack_split():
+    x = Batch(a=np.ones((3, 2)), b=Batch(c=np.arange(3)))
+    y = Batch(a=np.zeros((2, 2)), b=Batch(c=np.arange(2)), only=np.array([5.0, 6.0]))
+    z = Batch.cat([x, y])
+    assert z.a.shape == (5, 2) and z.b.c.tolist() == [0, 1, 2, 0, 1]
+    assert z.only.tolist() == [0, 0, 0, 5, 6]           # partial keys are zero padded
+    s = Batch.stack([Batch(a=1.0, b=np.array([1, 2])), Batch(a=2.0, b=np.array([3, 4]))])
+    assert s.a.tolist() == [1, 2] and s.b.shape == (2, 2)
+    lst = Batch([{"a": 1, "b": {"c": 2.0}}, {"a": 3, "b": {"c": 4.0}}])
+    assert lst.a.tolist() == [1, 3] and lst.b.c.tolist() == [2.0, 4.0]
+    np.random.seed(0)
+    parts = list(Batch(v=np.arange(10)).split(4, shuffle=True, merge_last=True))
+    np.random.seed(0)
+    perm = np.random.permutation(10)
+    assert [len(p) for p in parts] == [4, 6]
+    assert np.array_equal(np.concatenate([p.v for p in parts]), perm)
+    assert [len(p) for p in Batch(v=np.arange(10)).split(4, shuffle=False)] == [4, 4, 2]
+    assert [len(p) for p in Batch(v=np.arange(10)).split(-1)] == [10]
+
+
+@pytest.mark.parametrize("n,size", [(10, 4), (8, 4), (5, 10), (1, 1), (524288, 16384), (100, 33), (12, 5)])
+def test_minibatch_bounds_match_reference_rule(n, size):
+    """Same chunking as Batch.split (tianshou/data/batch.py:1199-1215)."""
+    got = minibatch_bounds(n, size, merge_last=True)
+    merge = n % size > 0
+    exp = []
+    for idx in range(0, n, size):
+        if merge and idx + size + size >= n:
+            exp.append((idx, n)); break
+        exp.append((idx, min(idx + size, n)))
+    assert got == exp and got[0][0] == 0 and got[-1][1] == n
+
+
+def test_batch_to_torch_numpy_and_null():
+    b = Batch(a=np.array([1.0, np.nan]), b=Batch(c=np.array([1, 2])))
+    assert b.hasnull()
+    assert not Batch(a=np.array([1.0, 2.0])).hasnull()
+    t = b.to_torch()
+    assert isinstance(t.a, torch.Tensor) and isinstance(t.b.c, torch.Tensor)
+    assert isinstance(t.to_numpy().a, np.ndarray)
+    assert len(b.dropnull()) == 1
+
+
+# ------------------------------------------------------------------------------- buffers (host)
+def test_vector_buffer_add_matches_reference_bookkeeping():
+    """Vectorised add == the reference's per-child state machine (golden: states after scripted adds)."""
+    g = load_golden("index_ref.npz")
+    rng = np.random.default_rng(77)
+    from oracle.gen_golden_replay import replay_index_cases   # deterministic replay of the generator script
+    for c, (buf, exp) in enumerate(replay_index_cases(rng, VectorReplayBuffer, Batch)):
+        p = f"idx{c}_"
+        assert np.array_equal(buf.last_index, g[p + "last_index"]), c
+        assert np.array_equal(buf._sizes, g[p + "lengths"]), c
+        assert np.array_equal(np.asarray(buf.done, dtype=bool), g[p + "done"]), c
+        # host RNG streams: manager RandomState(42) + one RandomState(42) per sub-buffer
+        assert np.array_equal(buf.sample_indices(37), g[p + "sample37"]), c
+        assert np.array_equal(buf.sample_indices(5), g[p + "sample5"]), c
+
+
+def test_buffer_episode_statistics_and_reset():
+    buf = VectorReplayBuffer(12, 3)
+    for t in range(5):
+        done = np.array([t == 2, False, t == 4])
+        idx, ep_ret, ep_len, ep_start = buf.add(
+            Batch(obs=np.zeros((3, 2)), act=np.zeros(3), rew=np.array([1.0, 2.0, 3.0]), terminated=done,
+                  truncated=np.zeros(3, bool), obs_next=np.zeros((3, 2))))
+        if t == 2:
+            assert ep_ret.tolist() == [3.0, 0.0, 0.0] and ep_len.tolist() == [3, 0, 0] and ep_start.tolist() == [0, 4, 8]
+        if t == 4:
+            assert ep_ret.tolist() == [0.0, 0.0, 15.0] and ep_len.tolist() == [0, 0, 5]
+            assert idx.tolist() == [0, 4, 8]          # capacity 4 per env: wrapped
+    assert len(buf) == 12 and buf.rew.dtype == np.float64 and buf.done.dtype == np.bool_
+    buf.reset(keep_statistics=True)
+    assert len(buf) == 0 and buf._ep_len.tolist() == [2, 5, 0]
+    buf.reset()
+    assert buf._ep_len.tolist() == [0, 0, 0]
+    with pytest.raises(AssertionError):
+        buf.rew = 1
+
+
+def test_single_buffer_add_and_sample_stream():
+    buf = ReplayBuffer(5)
+    for i in range(7):
+        idx, ep_ret, ep_len, ep_start = buf.add(Batch(obs=i, act=i, rew=float(i), terminated=i == 3, truncated=False))
+    assert len(buf) == 5 and buf.last_index.tolist() == [1] and buf._insertion_idx == 2
+    assert buf.rew.tolist() == [5.0, 6.0, 2.0, 3.0, 4.0]
+    ref = np.random.RandomState(42).choice(5, 4)
+    assert np.array_equal(buf.sample_indices(4), ref)
+    assert buf.sample_indices(-1).tolist() == []
+    with pytest.raises(ValueError):
+        buf.add(Batch(obs=1, act=1, rew=1.0, terminated=False, truncated=False), buffer_ids=[1, 2])
+
+
+def test_device_path_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tianshou_b200._cabi import ExtensionMissingError
+    buf = ReplayBuffer(5)
+    buf.add(Batch(obs=1, act=1, rew=1.0, terminated=False, truncated=False))
+    with pytest.raises(ExtensionMissingError):
+        buf.next(np.array([0]))
+    with pytest.raises(ExtensionMissingError):
+        buf.sample_indices(0)
+
+
+# ------------------------------------------------------------------------------------ C ABI
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "ts_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ts_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from tianshou_b200 import _cabi
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ts_b200.h but not exported"
+    bound = set(_cabi.SIGNATURES) | set(_cabi.OTHER_SYMBOLS)
+    assert set(names) == bound, set(names) ^ bound
+    lib2 = _cabi.load_library()
+    assert lib2.ts_version() == 1
+    assert lib2.ts_gae_workspace_bytes(2048 * 3 + 1) > 0
+
+
+def test_cabi_struct_layouts_match_header():
+    from tianshou_b200._cabi import ActorCriticDesc, PPOHParams
+    assert ctypes.sizeof(ActorCriticDesc) == 4 * 4 + 14 * 8
+    assert ctypes.sizeof(PPOHParams) == 11 * 8 + 3 * 4 + 4      # trailing pad to 8

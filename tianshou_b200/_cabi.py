@@ -53,7 +53,8 @@ _D = C.c_double
 
 # name -> argtypes (restype is int unless noted); mirrors include/ts_b200.h one to one
 SIGNATURES: dict[str, list[Any]] = {
-    "ts_gae": [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _I64, _D, _D, _P, _D, _P, _P, C.c_int, _P, _P],
+    "ts_gae": [_P, _P, C.c_int, _P, _P, _P, _P, C.c_int, _I64, _D, _D, _P, _D, _P, _P, _P, C.c_int, _P, _P],
+    "ts_rms_merge": [_P, _P, _I32, _P],
     "ts_nstep_return": [_P, _P, _P, _P, _I64, _I64, _I32, _D, _P, C.c_int, _P],
     "ts_buffer_end_flags": [_P, _P, _P, _P, _I64, _P, _P],
     "ts_value_mask_rows": [_P, _P, _P, _I64, _I64, _P],

@@ -1,0 +1,180 @@
+"""PPO with the whole ``update()`` on the device.
+
+Reference: tianshou/algorithm/modelfree/ppo.py:16-224 (constructor kwargs :19-37, logp_old
+:146-162, minibatch loop :164-224).
+
+Per ``update(buffer, batch_size, repeat)``:
+  host : bulk H2D of the rollout (``_sample``), ``np.random.permutation`` per repeat (the
+         reference's *global numpy RNG* draw of ``Batch.split``, batch.py:1209, kept so that
+         minibatch composition is bit-identical), one D2H of the per-step loss table.
+  GPU  : critic x2 -> GAE scan (+ return scaling + RunningMeanStd) -> actor log-prob, then for
+         every minibatch: fused forward/backward + loss (``ts_ppo_grad``), global-norm clip +
+         Adam (``ts_clip_adam_step``).  With >1 ranks each rank processes its slice of the
+         minibatch and one all-reduce of (gradient, loss sums) precedes the Adam step.
+
+``minibatch_shuffle="device"`` replaces the host permutation by a keyed bijection generated on
+the GPU (``ts_make_permutation``); the update is then a single asynchronous C call.  The index
+stream then differs from the reference's (same distribution, different RNG) -- opt-in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Literal
+
+import numpy as np
+import torch
+
+from ... import ops
+from ..._cabi import STATS_STRIDE, call, ptr, stream_ptr
+from ...data import Batch, ReplayBuffer
+from ...data.batch import minibatch_bounds
+from ...parallel import allreduce_sum_, shard_bounds, world
+from ..optim import OptimizerFactory
+from .a2c import A2CTrainingStats, ActorCriticOnPolicyAlgorithm
+from .reinforce import ProbabilisticActorPolicy
+
+
+class PPO(ActorCriticOnPolicyAlgorithm):
+    """Proximal Policy Optimization (arXiv:1707.06347), clip variant with optional dual clip,
+    value clip, advantage normalisation and per-repeat advantage recomputation."""
+
+    def __init__(
+        self,
+        *,
+        policy: ProbabilisticActorPolicy,
+        critic: torch.nn.Module,
+        optim: OptimizerFactory,
+        eps_clip: float = 0.2,
+        dual_clip: float | None = None,
+        value_clip: bool = False,
+        advantage_normalization: bool = True,
+        recompute_advantage: bool = False,
+        vf_coef: float = 0.5,
+        ent_coef: float = 0.01,
+        max_grad_norm: float | None = None,
+        gae_lambda: float = 0.95,
+        max_batchsize: int = 256,
+        gamma: float = 0.99,
+        return_scaling: bool = False,
+        minibatch_shuffle: Literal["numpy", "device"] = "numpy",
+        shuffle_seed: int = 0,
+    ) -> None:
+        assert dual_clip is None or dual_clip > 1.0, (
+            f"Dual-clip PPO parameter should greater than 1.0 but got {dual_clip}")
+        super().__init__(policy=policy, critic=critic, optim=optim, optim_include_actor=True,
+                         max_grad_norm=max_grad_norm, gae_lambda=gae_lambda, max_batchsize=max_batchsize,
+                         gamma=gamma, return_scaling=return_scaling)
+        self.vf_coef = vf_coef
+        self.ent_coef = ent_coef
+        self.eps_clip = eps_clip
+        self.dual_clip = dual_clip
+        self.value_clip = value_clip
+        self.advantage_normalization = advantage_normalization
+        self.recompute_adv = recompute_advantage
+        if minibatch_shuffle not in ("numpy", "device"):
+            raise ValueError(f"minibatch_shuffle must be 'numpy' or 'device', got {minibatch_shuffle!r}")
+        self.minibatch_shuffle = minibatch_shuffle
+        self._shuffle_seed = shuffle_seed
+        self._shuffle_epoch = 0
+
+    # ------------------------------------------------------------------ preprocess
+    def _preprocess_batch(self, batch: Batch, buffer: ReplayBuffer, indices: Any) -> Batch:
+        """returns / advantages / logp_old on the device (ppo.py:146-162)."""
+        self._rms_begin()
+        if self.recompute_adv:
+            self._buffer, self._indices = buffer, indices
+        batch = self._add_returns_and_advantages(batch, buffer, indices)
+        n = batch.obs.shape[0]
+        logp_old = self._buf("logp_old", n, torch.float32)
+        ops.actor_logp(self._flat.flat, self._desc, batch.obs, batch.act, out=logp_old)
+        batch.__dict__["logp_old"] = logp_old
+        return batch
+
+    def _ppo_hparams(self):
+        return self._hparams(
+            eps_clip=float(self.eps_clip), dual_clip=float(self.dual_clip or 0.0), vf_coef=float(self.vf_coef),
+            ent_coef=float(self.ent_coef), value_clip=int(bool(self.value_clip)),
+            advantage_normalization=int(bool(self.advantage_normalization)))
+
+    # ------------------------------------------------------------------ update
+    def _update_with_batch(self, batch: Batch, batch_size: int | None, repeat: int) -> A2CTrainingStats:
+        """The repeat x minibatch loop of ppo.py:164-224 as device work."""
+        dev = self.device
+        N = batch.obs.shape[0]
+        size = batch_size or N
+        bounds = minibatch_bounds(N, size, merge_last=True)
+        n_mb = len(bounds)
+        hp = self._ppo_hparams()
+        stats = self._alloc_stats(repeat * n_mb)
+        rank, wsize = world()
+        single_call = self.minibatch_shuffle == "device" and wsize == 1
+
+        if self.minibatch_shuffle == "device":
+            perms = ops.make_permutation(self._shuffle_seed, self._shuffle_epoch, repeat, N, dev)
+            self._shuffle_epoch += repeat
+        else:
+            perms = None
+
+        adv_tmp = self._buf("adv_tmp", 32, torch.uint8)
+        adv_tmp.zero_()
+        bounds_c = (C.c_int64 * (2 * n_mb))(*[x for b in bounds for x in b])
+
+        def run_repeats(perm_rows: torch.Tensor, r0: int, nrep: int, recompute: bool) -> None:
+            f = self._flat
+            call("ts_ppo_update", ptr(f.flat), ptr(f.grad), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
+                 C.byref(self._desc), C.byref(hp), ptr(batch.obs), ptr(batch.obs_next), ptr(batch.act),
+                 ptr(batch.rew), ptr(batch.terminated), ptr(batch.truncated), ptr(batch.get("_unfinished")),
+                 ptr(batch.v_s), ptr(batch.returns), ptr(batch.adv), ptr(batch.logp_old),
+                 ptr(self._buf("v_next", N, torch.float32)), N, ptr(perm_rows), nrep, bounds_c, n_mb,
+                 int(recompute), float(self.gamma), float(self.gae_lambda),
+                 ptr(self._rms_device()) if self.return_scaling else None, float(self._eps),
+                 ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(stats[r0 * n_mb:]), stream_ptr(dev))
+
+        if single_call:
+            run_repeats(perms, 0, repeat, self.recompute_adv)
+        else:
+            host_perm = None
+            for r in range(repeat):
+                if self.recompute_adv and r > 0:
+                    self._add_returns_and_advantages(batch, None, None)
+                if perms is None:
+                    # the reference's RNG draw, overlapped with the GPU work enqueued so far
+                    order = np.random.permutation(N).astype(np.int32)
+                    host_perm = torch.from_numpy(order)
+                    if torch.cuda.is_available():
+                        host_perm = host_perm.pin_memory()
+                    perm_r = host_perm.to(dev, non_blocking=True)
+                else:
+                    perm_r = perms[r]
+                if wsize == 1:
+                    run_repeats(perm_r, r, 1, False)
+                else:
+                    self._distributed_repeat(batch, perm_r, bounds, hp, stats[r * n_mb:], rank, wsize)
+        result = self._stats_from_device(stats)   # the only host sync of the update
+        self._rms_end()
+        self._flat.export_state(self.optim._optim)
+        return result
+
+    def _distributed_repeat(self, batch: Batch, perm: torch.Tensor, bounds: list[tuple[int, int]], hp: Any,
+                            stats: torch.Tensor, rank: int, wsize: int) -> None:
+        """One pass over the minibatches with the gradient all-reduce between backward and Adam.
+        Every rank owns ITS OWN rollout shard (weak scaling): the global minibatch is the union of
+        the ranks' local minibatches, so the mean's denominator is wsize * local rows."""
+        f, dev = self._flat, self.device
+        st = stream_ptr(dev)
+        for m, (lo, hi) in enumerate(bounds):
+            global_rows = (hi - lo) * wsize
+            adv_mom = None
+            if self.advantage_normalization:
+                sums = self._buf("adv_sums", 2, torch.float64)
+                sums.zero_()
+                call("ts_minibatch_adv_sums", ptr(batch.adv), ptr(perm), lo, hi, ptr(sums), st)
+                allreduce_sum_(sums)
+                adv_mom = self._buf("adv_mom", 2, torch.float32)
+                call("ts_adv_moments_finalize", ptr(sums), global_rows, ptr(adv_mom), st)
+            call("ts_ppo_grad", ptr(f.flat), C.byref(self._desc), C.byref(hp), ptr(batch.obs), ptr(batch.act),
+                 ptr(batch.adv), ptr(batch.returns), ptr(batch.logp_old), ptr(batch.v_s), ptr(perm), lo, hi,
+                 global_rows, ptr(adv_mom), ptr(f.grad), st)
+            allreduce_sum_(f.grad)   # ONE collective per optimiser step: grads + loss sums
+            call("ts_clip_adam_step", ptr(f.flat), ptr(f.grad), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
+                 C.byref(self._desc), C.byref(hp), ptr(stats[m]), st)

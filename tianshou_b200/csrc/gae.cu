@@ -51,6 +51,7 @@ struct GaeParams {
     int num_tiles;
     double gamma, lam;
     double* rms;  // {mean, var, count} or null
+    double* batch_moments;  // {count, mean, M2} of this call's un-scaled returns, or null
     double rms_eps;
     void* adv_out;
     void* ret_out;
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
     }
     __syncthreads();
 
+    const bool want_moments = (p.rms != nullptr) || (p.batch_moments != nullptr);
     double g = eB + eA * s_carry;  // adv just right of this thread's items
     double advv[kItems], retv[kItems];
     double mn = 0.0, mm = 0.0, mM = 0.0;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
         advv[j] = g;
         const double r = g + vs[j];  // un-scaled return (algorithm_base.py:717)
         retv[j] = r / scale;          // a2c.py:146
-        if (p.rms && base + j < p.n) {
+        if (want_moments && base + j < p.n) {
             mn += 1.0;
             const double dl = r - mm;
             mm += dl / mn;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
         }
     }
 
-    if (p.rms == nullptr) return;
+    if (!want_moments) return;
     // (count, mean, M2) of un-scaled returns: warp -> CTA -> (last CTA) whole array
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -348,7 +350,9 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
         const double M2 = tsb::shfl_down_f64(M1, off);
         if (lane + off < 32) chan_merge(n1, m1, M1, n2, m2, M2);
     }
-    if (lane == 0 && n1 > 0.0) {
+    if (lane == 0 && p.batch_moments) {  // multi-GPU: the caller merges moments across ranks
+        p.batch_moments[0] = n1; p.batch_moments[1] = m1; p.batch_moments[2] = M1;
+    } else if (lane == 0 && n1 > 0.0) {
         // utils/statistics.py:99-114
         const double batch_mean = m1, batch_var = M1 / n1, batch_count = n1;
         const double mean = p.rms[0], var = p.rms[1], count = p.rms[2];
@@ -369,6 +373,28 @@ inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7
 
 }  // namespace
 
+namespace {
+__global__ void rms_merge_kernel(double* __restrict__ rms, const double* __restrict__ moments, int parts) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double n1 = 0.0, m1 = 0.0, M1 = 0.0;
+    for (int k = 0; k < parts; ++k) chan_merge(n1, m1, M1, moments[3 * k], moments[3 * k + 1], moments[3 * k + 2]);
+    if (n1 <= 0.0) return;
+    const double batch_mean = m1, batch_var = M1 / n1, batch_count = n1;
+    const double mean = rms[0], var = rms[1], count = rms[2];
+    const double delta = batch_mean - mean;
+    const double total = count + batch_count;
+    rms[0] = mean + delta * batch_count / total;
+    rms[1] = (var * count + batch_var * batch_count + delta * delta * count * batch_count / total) / total;
+    rms[2] = total;
+}
+}  // namespace
+
+extern "C" int ts_rms_merge(double* rms_state, const double* moments, int32_t parts, ts_stream_t stream) {
+    TS_REQUIRE(rms_state && moments && parts >= 1, "ts_rms_merge: bad arguments");
+    rms_merge_kernel<<<1, 32, 0, tsb::as_stream(stream)>>>(rms_state, moments, parts);
+    return tsb::check_launch("ts_rms_merge");
+}
+
 extern "C" size_t ts_gae_workspace_bytes(int64_t n) {
     const int64_t tiles = (n + kTile - 1) / kTile;
     return sizeof(WsHeader) + (size_t)tiles * (sizeof(TileState) + sizeof(TileMoments));
@@ -377,8 +403,9 @@ extern "C" size_t ts_gae_workspace_bytes(int64_t n) {
 extern "C" int ts_gae(const void* v_s, const void* v_s_next, int v_dtype, const double* rew,
                       const uint8_t* terminated, const uint8_t* truncated,
                       const uint8_t* extra_end, int terminated_ends, int64_t n, double gamma,
-                      double lam, double* rms_state, double rms_eps, void* adv_out, void* ret_out,
-                      int out_dtype, void* workspace, ts_stream_t stream) {
+                      double lam, double* rms_state, double rms_eps, double* batch_moments_out,
+                      void* adv_out, void* ret_out, int out_dtype, void* workspace,
+                      ts_stream_t stream) {
     TS_REQUIRE(n >= 0, "ts_gae: negative n");
     if (n == 0) return 0;
     TS_REQUIRE(v_s && v_s_next && rew && adv_out && ret_out && workspace, "ts_gae: null pointer");
@@ -393,7 +420,7 @@ extern "C" int ts_gae(const void* v_s, const void* v_s_next, int v_dtype, const 
     p.n = n;
     p.num_tiles = (int)((n + kTile - 1) / kTile);
     p.gamma = gamma; p.lam = lam;
-    p.rms = rms_state; p.rms_eps = rms_eps;
+    p.rms = rms_state; p.rms_eps = rms_eps; p.batch_moments = batch_moments_out;
     p.adv_out = adv_out; p.ret_out = ret_out;
     p.vec_ok = aligned16(v_s) && aligned16(v_s_next) && aligned16(rew) && aligned16(adv_out) &&
                aligned16(ret_out) && (!terminated || aligned8(terminated)) &&

@@ -783,7 +783,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* exp_avg, float* 
             TS_REQUIRE(obs_next && rew && v_next_tmp && gae_ws, "ts_ppo_update: recompute needs obs_next/rew/scratch");
             if (int e = ts_critic_forward(params, desc, obs, v_s, obs_next, v_next_tmp, N, stream)) return e;
             if (int e = ts_gae(v_s, v_next_tmp, TS_F32, rew, terminated, truncated, extra_end, 1, N, gamma,
-                               lam, rms_state, rms_eps, adv, returns, TS_F32, gae_ws, stream)) return e;
+                               lam, rms_state, rms_eps, nullptr, adv, returns, TS_F32, gae_ws, stream)) return e;
         }
         const int32_t* pr = perm ? perm + (int64_t)r * N : nullptr;
         for (int m = 0; m < n_minibatch; ++m) {

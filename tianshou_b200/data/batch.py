@@ -261,6 +261,8 @@ class Batch:
         if not set(value.keys()).issubset(self.__dict__.keys()):
             raise ValueError("Creating keys is not supported by item assignment.")
         for k, cur in self.__dict__.items():
+            if cur is None:
+                continue
             if k in value.__dict__:
                 cur[index] = value.__dict__[k]
             elif isinstance(cur, Batch):

@@ -61,6 +61,7 @@ def gae(
     device: torch.device | str | None = None,
     workspace: torch.Tensor | None = None,
     out: tuple[torch.Tensor, torch.Tensor] | None = None,
+    batch_moments_out: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """(advantages, returns) -- see ``ts_gae`` in include/ts_b200.h.
     Reference: algorithm_base.py:704-719,1085-1140; a2c.py:131-152."""
@@ -82,7 +83,7 @@ def gae(
         workspace = torch.empty(max(need, 64), dtype=torch.uint8, device=dev)
     call("ts_gae", ptr(v_s), ptr(v_s_next), _dt(v_s.dtype), ptr(rew), ptr(term), ptr(trunc), ptr(extra),
          int(terminated_ends), n, float(gamma), float(gae_lambda), ptr(rms_state), float(rms_eps),
-         ptr(adv), ptr(ret), _dt(adv.dtype), ptr(workspace), stream_ptr(dev))
+         ptr(batch_moments_out), ptr(adv), ptr(ret), _dt(adv.dtype), ptr(workspace), stream_ptr(dev))
     return adv, ret
 
 
@@ -150,12 +151,18 @@ def stack_next_indices(meta: DeviceBufferMeta, index: np.ndarray | torch.Tensor,
     return out
 
 
-def unfinished_index(meta: DeviceBufferMeta) -> torch.Tensor:
-    """Ordered unfinished slots (device int64[count]); one D2H of the count."""
+def unfinished_index_raw(meta: DeviceBufferMeta) -> tuple[torch.Tensor, torch.Tensor]:
+    """(slots[E], count[1]) on the device, no host sync (manager.py:85-91)."""
     out = torch.empty(meta.E, dtype=torch.int64, device=meta.device)
     cnt = torch.zeros(1, dtype=torch.int64, device=meta.device)
     o, E, d, l, n = meta._args()
     call("ts_unfinished_index", o, E, d, l, n, ptr(out), ptr(cnt), stream_ptr(meta.device))
+    return out, cnt
+
+
+def unfinished_index(meta: DeviceBufferMeta) -> torch.Tensor:
+    """Ordered unfinished slots (device int64[count]); one D2H of the count."""
+    out, cnt = unfinished_index_raw(meta)
     return out[: int(cnt.item())]
 
 
@@ -177,13 +184,14 @@ def buffer_end_flags(meta: DeviceBufferMeta) -> torch.Tensor:
 
 
 def mark_members(idx: torch.Tensor, members: torch.Tensor, table_size: int,
-                 table: torch.Tensor | None = None) -> torch.Tensor:
-    """np.isin(idx, members) as uint8 (algorithm_base.py:715)."""
+                 table: torch.Tensor | None = None, count: torch.Tensor | None = None) -> torch.Tensor:
+    """np.isin(idx, members[:count]) as uint8 (algorithm_base.py:715); ``count`` is an optional
+    device int64[1] so that no host sync is needed for a variable-length member list."""
     dev = idx.device
     if table is None:
         table = torch.zeros(table_size, dtype=torch.uint8, device=dev)
     out = torch.empty(idx.numel(), dtype=torch.uint8, device=dev)
-    call("ts_mark_members", ptr(idx), idx.numel(), ptr(members) if members.numel() else None, None,
+    call("ts_mark_members", ptr(idx), idx.numel(), ptr(members) if members.numel() else None, ptr(count),
          members.numel(), ptr(table), table.numel(), ptr(out), stream_ptr(dev))
     return out
 
