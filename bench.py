@@ -115,6 +115,12 @@ def cpu_reference_run(E: int, T: int, steps: int, warmup: int) -> dict:
     same minibatch size / repeat / hyper-parameters; all host threads numpy's BLAS will use."""
     from oracle import oracle_np as onp
     from tianshou_b200.synthetic import synth_rollout
+    try:  # the reference's `_gae` is compiled (numba): use the C restatement, not the Python loop
+        from oracle import oracle_c
+        oracle_c.lib()
+        onp.gae = lambda v_s, v_s_, rew, end, gamma, lam: oracle_c.gae(v_s, v_s_, rew, end, gamma, lam)
+    except OSError:
+        pass
     rng = np.random.default_rng(0)
     cols: dict[str, list] = {k: [] for k in ("obs", "act", "rew", "terminated", "truncated", "obs_next")}
     for s in synth_rollout(rng, E, T, OBS, ACT):

@@ -266,6 +266,13 @@ int ts_make_permutation(uint64_t seed, int32_t first_epoch, int32_t n_epochs, in
 /* int64 -> int32 narrowing of a host-drawn permutation already uploaded to the device. */
 int ts_narrow_i64_i32(const int64_t* src, int64_t n, int32_t* dst, ts_stream_t stream);
 
+/* Hardware self-test of the tcgen05 / TMEM building blocks (csrc/umma.cuh), one CTA:
+ * D[M,N] = a[M,K] * b[N,K]^T with dtype 0 = 3xTF32 (kind::tf32) or 1 = 3-way bf16 split (kind::f16),
+ * M in {64,128}; a_mn / b_mn place the operand MN-major instead of K-major in shared memory; swap
+ * exchanges LBO/SBO (diagnostic).  d receives the RAW accumulator: 128 TMEM lanes x N columns. */
+int ts_umma_selftest(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K,
+                     int32_t dtype, int32_t a_mn, int32_t b_mn, int32_t swap, ts_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,13 +86,13 @@ def test_ppo_grad_kernel_vs_oracle(variant):
     f = algo._flat
     f.grad.zero_()
     adv_mom = None
+    d_obs, d_act, d_adv, d_ret, d_lpo, d_vs, d_perm = t(obs), t(act), t(adv), t(ret), t(logp_old), t(v_s), t(perm)
     if hp.advantage_normalization:
         sums = torch.zeros(2, dtype=torch.float64, device=DEV)
         adv_mom = torch.zeros(2, dtype=torch.float32, device=DEV)
-        call("ts_minibatch_adv_sums", ptr(t(adv)), ptr(t(perm)), lo, hi, ptr(sums), stream_ptr())
+        call("ts_minibatch_adv_sums", ptr(d_adv), ptr(d_perm), lo, hi, ptr(sums), stream_ptr())
         call("ts_adv_moments_finalize", ptr(sums), hi - lo, ptr(adv_mom), stream_ptr())
         np.testing.assert_allclose(adv_mom.cpu().numpy(), [adv[idx].mean(), adv[idx].std(ddof=1)], rtol=1e-5)
-    d_obs, d_act, d_adv, d_ret, d_lpo, d_vs, d_perm = t(obs), t(act), t(adv), t(ret), t(logp_old), t(v_s), t(perm)
     call("ts_ppo_grad", ptr(f.flat), C.byref(algo._desc), C.byref(hp), ptr(d_obs), ptr(d_act), ptr(d_adv), ptr(d_ret),
          ptr(d_lpo), ptr(d_vs), ptr(d_perm), lo, hi, hi - lo, ptr(adv_mom), ptr(f.grad), stream_ptr())
     got = f.grad.cpu().numpy()
@@ -188,7 +188,10 @@ def test_state_dict_round_trip_and_module_views():
         assert torch.equal(a, b), k
     assert torch.equal(algo._flat.exp_avg, algo2._flat.exp_avg) and torch.equal(algo._flat.exp_avg_sq, algo2._flat.exp_avg_sq)
     assert int(algo2._flat.step.item()) == 4
-    # both continue identically
+    # both continue identically (the running return statistics are a plain attribute, not part of the
+    # state_dict -- in the reference too, a2c.py:112)
+    import copy
+    algo2.ret_rms = copy.deepcopy(algo.ret_rms)
     for a in (algo, algo2):
         np.random.seed(7)
         with policy_within_training_step(a.policy):
