@@ -301,13 +301,14 @@ def main() -> None:
     reps = 40
     rows = min(BATCH_SIZE, N)
     grad_events = []
+    n_part = C.c_int32(0)
     for i in range(reps + 5):
         lo = (i * rows) % max(1, N - rows + 1)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         call("ts_ppo_grad", ptr(f.flat), C.byref(algo._desc), C.byref(hp), ptr(b.obs), ptr(b.act), ptr(b.adv),
-             ptr(b.returns), ptr(b.logp_old), ptr(b.v_s), ptr(perm), lo, lo + rows, rows, None, ptr(f.grad),
-             stream_ptr(dev))
+             ptr(b.returns), ptr(b.logp_old), ptr(b.v_s), ptr(perm), lo, lo + rows, rows, None, ptr(f.partials),
+             C.byref(n_part), stream_ptr(dev))
         e.record()
         if i >= 5:
             grad_events.append((s, e))
@@ -361,7 +362,7 @@ def main() -> None:
                           "note": "public API with minibatch_shuffle='numpy': np.random.permutation per repeat on the host "
                                   "(bit-identical minibatch composition to the reference)"},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "ppo_grad_kernel (fused minibatch fwd/bwd, fp32 SIMT)", "bound": "tensor",
+        "roofline": {"kernel": "ppo_grad_tc_kernel (fused minibatch fwd/bwd, tcgen05 bf16x3 = fp32-faithful)", "bound": "tensor",
                      "achieved": grad_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": grad_tflops / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_flops_per_launch": grad_flops, "launch_ms": grad_ms, "rows_per_launch": rows},

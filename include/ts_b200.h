@@ -215,16 +215,23 @@ typedef struct ts_ppo_hparams {
 #define TS_PPO_GRAD_EXTRA 4
 
 /* One minibatch forward/backward (ppo.py:179-211 + loss.backward of algorithm_base.py:497):
- * rows are perm[lo..hi) of the rollout tensors; ACCUMULATES d(loss)/d(params) * (local_rows /
- * global_rows weighting is the caller's: gradients are sums scaled by 1/global_rows) into grad
- * and the loss sums into grad[n_params..].  `global_rows` is the minibatch size over all ranks
- * (the mean's denominator); adv_moments: device float[2] = {mean, std} when
+ * rows are perm[lo..hi) of the rollout tensors.  Every CTA writes ITS OWN partial sum of
+ * d(loss)/d(params) (already scaled by 1/global_rows) and of the four loss sums into row
+ * blockIdx.x of `partials` ([ts_ppo_partial_rows()][n_params + TS_PPO_GRAD_EXTRA] floats) -- no
+ * cross-CTA atomics, deterministic.  *n_partials_out (host) receives the number of rows written;
+ * they are folded by ts_grad_reduce / ts_clip_adam_step.  `global_rows` is the minibatch size
+ * over all ranks (the mean's denominator); adv_moments: device float[2] = {mean, std} when
  * advantage_normalization, else NULL.  perm may be NULL (identity). */
+int32_t ts_ppo_partial_rows(void);
 int ts_ppo_grad(const float* params, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
                 const float* obs, const float* act, const float* adv, const float* ret,
                 const float* logp_old, const float* v_s, const int32_t* perm, int64_t lo,
-                int64_t hi, int64_t global_rows, const float* adv_moments, float* grad,
-                ts_stream_t stream);
+                int64_t hi, int64_t global_rows, const float* adv_moments, float* partials,
+                int32_t* n_partials_out /* host */, ts_stream_t stream);
+/* grad[i] = sum_p partials[p][i] (fixed order) for i < n_params + TS_PPO_GRAD_EXTRA: the flat
+ * gradient + loss sums a multi-GPU caller all-reduces before ts_clip_adam_step. */
+int ts_grad_reduce(const float* partials, int32_t n_partials, const ts_actor_critic_desc* desc,
+                   float* grad, ts_stream_t stream);
 /* mean and unbiased std of adv[perm[lo..hi)] (ppo.py:184-186) -> out[0..1]; partial sums go to
  * sums (device double[2]) first so a multi-GPU caller can allreduce them; pass finalize=1 to
  * turn (sum, sumsq, count=global_rows) into {mean, std}. */
@@ -232,12 +239,16 @@ int ts_minibatch_adv_sums(const float* adv, const int32_t* perm, int64_t lo, int
                           double* sums, ts_stream_t stream);
 int ts_adv_moments_finalize(const double* sums, int64_t global_rows, float* out,
                             ts_stream_t stream);
-/* clip_grad_norm_ + Adam.step + zero_grad (algorithm_base.py:496-500; torch/optim/adam.py
- * single-tensor path) on the flat buffers, and one row of per-step statistics.
- * step_count: device int64[1], incremented.  stats_row: device float[TS_PPO_STATS_STRIDE]. */
-int ts_clip_adam_step(float* params, float* grad, float* exp_avg, float* exp_avg_sq,
-                      int64_t* step_count, const ts_actor_critic_desc* desc,
-                      const ts_ppo_hparams* hp, float* stats_row, ts_stream_t stream);
+/* clip_grad_norm_ + Adam.step (algorithm_base.py:496-500; torch/optim/adam.py single-tensor
+ * path) on the flat buffers, and one row of per-step statistics.  If partials != NULL the
+ * gradient is first folded from the n_partials rows (single-GPU fast path: reduce + norm + clip
+ * + Adam in ONE launch); otherwise `grad` must already hold the (all-reduced) gradient.
+ * grad: n_params + TS_PPO_GRAD_EXTRA floats (scratch / input).  step_count: device int64[1],
+ * incremented.  stats_row: device float[TS_PPO_STATS_STRIDE]. */
+int ts_clip_adam_step(float* params, float* grad, const float* partials, int32_t n_partials,
+                      float* exp_avg, float* exp_avg_sq, int64_t* step_count,
+                      const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp, float* stats_row,
+                      ts_stream_t stream);
 
 /* The whole single-GPU `PPO._update_with_batch` loop (ppo.py:164-224) on one stream:
  * for r in repeat: [recompute v_s/returns/adv (a2c.py:115-153)] ; for each minibatch of
@@ -247,9 +258,10 @@ int ts_clip_adam_step(float* params, float* grad, float* exp_avg, float* exp_avg
  * truncated, extra_end u8; v_s, returns, adv, logp_old f32 (in/out: must be valid on entry,
  * rewritten when recompute_adv).  stats: repeat*n_mb rows.  rms_state as in ts_gae (nullable
  * when return_scaling is off).  v_next_tmp: N f32 scratch.  gae_ws: ts_gae_workspace_bytes(N).
- * grad: n_params + TS_PPO_GRAD_EXTRA floats, zero on entry. adv_tmp: double[2]+float[2] bytes.
+ * grad: n_params + TS_PPO_GRAD_EXTRA floats scratch; partials: ts_ppo_partial_rows() rows of the
+ * same width.  adv_tmp: double[2]+float[2] bytes.
  */
-int ts_ppo_update(float* params, float* grad, float* exp_avg, float* exp_avg_sq,
+int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, float* exp_avg_sq,
                   int64_t* step_count, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
                   const float* obs, const float* obs_next, const float* act, const double* rew,
                   const uint8_t* terminated, const uint8_t* truncated, const uint8_t* extra_end,

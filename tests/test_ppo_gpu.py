@@ -93,8 +93,11 @@ def test_ppo_grad_kernel_vs_oracle(variant):
         call("ts_minibatch_adv_sums", ptr(d_adv), ptr(d_perm), lo, hi, ptr(sums), stream_ptr())
         call("ts_adv_moments_finalize", ptr(sums), hi - lo, ptr(adv_mom), stream_ptr())
         np.testing.assert_allclose(adv_mom.cpu().numpy(), [adv[idx].mean(), adv[idx].std(ddof=1)], rtol=1e-5)
+    n_part = C.c_int32(0)
     call("ts_ppo_grad", ptr(f.flat), C.byref(algo._desc), C.byref(hp), ptr(d_obs), ptr(d_act), ptr(d_adv), ptr(d_ret),
-         ptr(d_lpo), ptr(d_vs), ptr(d_perm), lo, hi, hi - lo, ptr(adv_mom), ptr(f.grad), stream_ptr())
+         ptr(d_lpo), ptr(d_vs), ptr(d_perm), lo, hi, hi - lo, ptr(adv_mom), ptr(f.partials), C.byref(n_part), stream_ptr())
+    assert n_part.value == 3          # 300 rows -> three 128-row tiles, one partial row each
+    call("ts_grad_reduce", ptr(f.partials), n_part.value, C.byref(algo._desc), ptr(f.grad), stream_ptr())
     got = f.grad.cpu().numpy()
     off = 0
     for k in PARAM_ORDER:

@@ -74,11 +74,12 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_critic_forward": [_P, C.POINTER(ActorCriticDesc), _P, _P, _P, _P, _I64, _P],
     "ts_actor_logp": [_P, C.POINTER(ActorCriticDesc), _P, _P, _I64, _P, _P, _P],
     "ts_ppo_grad": [_P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams), _P, _P, _P, _P, _P, _P, _P,
-                    _I64, _I64, _I64, _P, _P, _P],
+                    _I64, _I64, _I64, _P, _P, C.POINTER(_I32), _P],
+    "ts_grad_reduce": [_P, _I32, C.POINTER(ActorCriticDesc), _P, _P],
     "ts_minibatch_adv_sums": [_P, _P, _I64, _I64, _P, _P],
     "ts_adv_moments_finalize": [_P, _I64, _P, _P],
-    "ts_clip_adam_step": [_P, _P, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams), _P, _P],
-    "ts_ppo_update": [_P, _P, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams),
+    "ts_clip_adam_step": [_P, _P, _P, _I32, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams), _P, _P],
+    "ts_ppo_update": [_P, _P, _P, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams),
                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32,
                       C.POINTER(_I64), _I32, _I32, _D, _D, _P, _D, _P, _P, _P, _P],
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
@@ -86,7 +87,7 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_umma_selftest": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 OTHER_SYMBOLS = ["ts_version", "ts_last_error", "ts_launch_count", "ts_reset_launch_count",
-                 "ts_gae_workspace_bytes"]
+                 "ts_gae_workspace_bytes", "ts_ppo_partial_rows"]
 
 _lib: C.CDLL | None = None
 
@@ -113,6 +114,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ts_reset_launch_count.restype = None
     lib.ts_gae_workspace_bytes.argtypes = [_I64]
     lib.ts_gae_workspace_bytes.restype = C.c_size_t
+    lib.ts_ppo_partial_rows.restype = C.c_int32
     if path is None:
         _lib = lib
     return lib

@@ -101,6 +101,10 @@ class FlatParams:
         self.n = sum(p.numel() for p in params)
         self.flat = torch.empty(self.n, dtype=torch.float32, device=device)
         self.grad = torch.zeros(self.n + grad_extra, dtype=torch.float32, device=device)
+        # per-CTA partial gradient rows written by ts_ppo_grad (folded by ts_clip_adam_step)
+        from .._cabi import load_library
+        self.partial_rows = int(load_library().ts_ppo_partial_rows())
+        self.partials = torch.zeros((self.partial_rows, self.n + grad_extra), dtype=torch.float32, device=device)
         self.exp_avg = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.step = torch.zeros(1, dtype=torch.int64, device=device)

@@ -121,7 +121,7 @@ class PPO(ActorCriticOnPolicyAlgorithm):
 
         def run_repeats(perm_rows: torch.Tensor, r0: int, nrep: int, recompute: bool) -> None:
             f = self._flat
-            call("ts_ppo_update", ptr(f.flat), ptr(f.grad), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
+            call("ts_ppo_update", ptr(f.flat), ptr(f.grad), ptr(f.partials), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
                  C.byref(self._desc), C.byref(hp), ptr(batch.obs), ptr(batch.obs_next), ptr(batch.act),
                  ptr(batch.rew), ptr(batch.terminated), ptr(batch.truncated), ptr(batch.get("_unfinished")),
                  ptr(batch.v_s), ptr(batch.returns), ptr(batch.adv), ptr(batch.logp_old),
@@ -172,9 +172,11 @@ class PPO(ActorCriticOnPolicyAlgorithm):
                 allreduce_sum_(sums)
                 adv_mom = self._buf("adv_mom", 2, torch.float32)
                 call("ts_adv_moments_finalize", ptr(sums), global_rows, ptr(adv_mom), st)
+            n_part = C.c_int32(0)
             call("ts_ppo_grad", ptr(f.flat), C.byref(self._desc), C.byref(hp), ptr(batch.obs), ptr(batch.act),
                  ptr(batch.adv), ptr(batch.returns), ptr(batch.logp_old), ptr(batch.v_s), ptr(perm), lo, hi,
-                 global_rows, ptr(adv_mom), ptr(f.grad), st)
+                 global_rows, ptr(adv_mom), ptr(f.partials), C.byref(n_part), st)
+            call("ts_grad_reduce", ptr(f.partials), n_part.value, C.byref(self._desc), ptr(f.grad), st)
             allreduce_sum_(f.grad)   # ONE collective per optimiser step: grads + loss sums
-            call("ts_clip_adam_step", ptr(f.flat), ptr(f.grad), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
+            call("ts_clip_adam_step", ptr(f.flat), ptr(f.grad), None, 0, ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
                  C.byref(self._desc), C.byref(hp), ptr(stats[m]), st)

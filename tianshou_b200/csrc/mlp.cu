@@ -16,6 +16,7 @@
 // gradient buffer with one RED per parameter per CTA.  Loss sums ride in the same buffer so that
 // a multi-GPU caller needs exactly one allreduce per optimiser step.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -387,11 +388,14 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
     const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ adv,
     const float* __restrict__ ret, const float* __restrict__ logp_old, const float* __restrict__ v_s,
     const int32_t* __restrict__ perm, int64_t lo, int64_t hi, int64_t global_rows,
-    const float* __restrict__ adv_moments, float* __restrict__ grad) {
+    const float* __restrict__ adv_moments, float* __restrict__ partials) {
     extern __shared__ __align__(16) float sm[];
     const Layout L = make_layout(d.obs_dim, d.act_dim, 2);
     const int A = d.act_dim;
     const int tid = threadIdx.x;
+    // this CTA's private partial-gradient row (folded later by clip_adam_kernel / grad_reduce_kernel)
+    float* __restrict__ grad = partials + (size_t)blockIdx.x * (size_t)(d.n_params + TS_PPO_GRAD_EXTRA);
+    for (int64_t i = tid; i < d.n_params + TS_PPO_GRAD_EXTRA; i += kThreads) grad[i] = 0.0f;
     const NetGlobal ga = actor_global(d), gc = critic_global(d);
     stage_net(sm, L.actor, params, ga, d.obs_dim, L.KX, A, true, true);
     stage_net(sm, L.critic, params, gc, d.obs_dim, L.KX, 1, true, false);
@@ -531,15 +535,41 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
 }
 
 // ---- clip_grad_norm_ + Adam + stats + zero_grad : one CTA ------------------------------------
+// Grid barrier / reduction state of clip_adam_kernel (self-resetting; launches are stream-ordered).
+__device__ unsigned int g_adam_arrive = 0, g_adam_depart = 0;
+__device__ double g_adam_ss = 0.0;
+
+// gradient fold + clip_grad_norm_ + Adam in one launch, ~11 co-resident CTAs of 1024 threads, one
+// parameter per thread: (0) fold the per-CTA partial rows of this parameter in a fixed order
+// (coalesced across threads, L2 resident), (1) block sum of squares -> one f64 atomic per CTA,
+// (2) grid barrier, (3) norm, clip coefficient, Adam update of the own element.
 __global__ void __launch_bounds__(1024) clip_adam_kernel(
-    float* __restrict__ params, float* __restrict__ grad, float* __restrict__ exp_avg,
-    float* __restrict__ exp_avg_sq, int64_t* __restrict__ step_count, int64_t n_params,
-    const ts_ppo_hparams hp, float* __restrict__ stats_row) {
+    float* __restrict__ params, float* __restrict__ grad, const float* __restrict__ partials, int n_partials,
+    float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t* __restrict__ step_count,
+    int64_t n_params, const ts_ppo_hparams hp, float* __restrict__ stats_row) {
     __shared__ double s_red[32];
-    __shared__ float s_coef, s_norm;
+    __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
     const int tid = threadIdx.x;
-    double ss = 0.0;
-    for (int64_t i = tid; i < n_params; i += blockDim.x) { const double g = grad[i]; ss += g * g; }
+    const int64_t step = *step_count + 1;
+    const int64_t width = n_params + TS_PPO_GRAD_EXTRA;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
+    float g = 0.0f;
+    if (i < width) {
+        if (partials) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int p = 0;
+            for (; p + 8 <= n_partials; p += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] += __ldcg(partials + (int64_t)(p + u) * width + i);
+            }
+            for (; p < n_partials; ++p) acc[0] += __ldcg(partials + (int64_t)p * width + i);
+            g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            if (i >= n_params) grad[i] = g;          // loss sums, read by CTA 0 after the barrier
+        } else {
+            g = __ldcg(grad + i);
+        }
+    }
+    double ss = (i < n_params) ? (double)g * (double)g : 0.0;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ss += tsb::shfl_xor_f64(ss, off);
     if ((tid & 31) == 0) s_red[tid >> 5] = ss;
@@ -547,50 +577,70 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(
     if (tid == 0) {
         double t = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
-        const float total_norm = (float)sqrt(t);
+        atomicAdd(&g_adam_ss, t);
+        __threadfence();
+        atomicAdd(&g_adam_arrive, 1u);
+        while (*((volatile unsigned int*)&g_adam_arrive) < gridDim.x) {}
+        __threadfence();
+        const float total_norm = (float)sqrt(*((volatile double*)&g_adam_ss));
         float coef = 1.0f;
         if (hp.max_grad_norm > 0.0) {   // torch.nn.utils.clip_grad_norm_
             coef = (float)hp.max_grad_norm / (total_norm + 1e-6f);
             coef = fminf(coef, 1.0f);
         }
         s_coef = coef; s_norm = total_norm;
+        const double bc1 = 1.0 - pow(hp.beta1, (double)step);
+        const double bc2 = 1.0 - pow(hp.beta2, (double)step);
+        s_step_size = (float)(hp.lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
     }
     __syncthreads();
-    const float coef = s_coef;
-    const int64_t step = *step_count + 1;
-    const double bc1 = 1.0 - pow(hp.beta1, (double)step);
-    const double bc2 = 1.0 - pow(hp.beta2, (double)step);
-    const float step_size = (float)(hp.lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
     const float w1 = (float)(1.0 - hp.beta1), w2 = (float)(1.0 - hp.beta2);
     const float beta2 = (float)hp.beta2, adam_eps = (float)hp.adam_eps, wd = (float)hp.weight_decay;
-    for (int64_t i = tid; i < n_params; i += blockDim.x) {
-        float g = grad[i] * coef;
+    if (i < n_params) {
+        g *= coef;
         float p = params[i];
         if (wd != 0.0f) g = fmaf(wd, p, g);
         float m = exp_avg[i], v = exp_avg_sq[i];
         m = m + w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
-        v = v * beta2 + w2 * g * g;              // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        v = v * beta2 + w2 * g * g;                 // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
         const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
         p = p - step_size * (m / denom);            // addcdiv_(exp_avg, denom, -step_size)
         exp_avg[i] = m; exp_avg_sq[i] = v; params[i] = p;
-        grad[i] = 0.0f;
     }
-    __syncthreads();
     if (tid == 0) {
-        float* ex = grad + n_params;
-        const float rows = ex[3] > 0.0f ? ex[3] : 1.0f;
-        const float clip_loss = -ex[0] / rows;
-        const float vf_loss = ex[1] / rows;
-        const float ent_loss = ex[2] / rows;
-        if (stats_row) {
-            stats_row[0] = clip_loss + (float)hp.vf_coef * vf_loss - (float)hp.ent_coef * ent_loss;
-            stats_row[1] = clip_loss; stats_row[2] = vf_loss; stats_row[3] = ent_loss;
-            stats_row[4] = s_norm; stats_row[5] = ex[3]; stats_row[6] = 0.0f; stats_row[7] = 0.0f;
+        if (blockIdx.x == 0) {
+            const float e0 = __ldcg(grad + n_params), e1 = __ldcg(grad + n_params + 1);
+            const float e2 = __ldcg(grad + n_params + 2), e3 = __ldcg(grad + n_params + 3);
+            const float rows = e3 > 0.0f ? e3 : 1.0f;
+            const float clip_loss = -e0 / rows, vf_loss = e1 / rows, ent_loss = e2 / rows;
+            if (stats_row) {
+                stats_row[0] = clip_loss + (float)hp.vf_coef * vf_loss - (float)hp.ent_coef * ent_loss;
+                stats_row[1] = clip_loss; stats_row[2] = vf_loss; stats_row[3] = ent_loss;
+                stats_row[4] = s_norm; stats_row[5] = e3; stats_row[6] = 0.0f; stats_row[7] = 0.0f;
+            }
+            *step_count = step;
         }
-        ex[0] = ex[1] = ex[2] = ex[3] = 0.0f;
-        *step_count = step;
+        if (atomicAdd(&g_adam_depart, 1u) == gridDim.x - 1) {
+            g_adam_arrive = 0; g_adam_depart = 0; g_adam_ss = 0.0;
+            __threadfence();
+        }
     }
+}
+
+__global__ void grad_reduce_kernel(const float* __restrict__ partials, int n_partials, int64_t width,
+                                   float* __restrict__ grad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int p = 0;
+    for (; p + 8 <= n_partials; p += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] += __ldcg(partials + (int64_t)(p + u) * width + i);
+    }
+    for (; p < n_partials; ++p) acc[0] += __ldcg(partials + (int64_t)p * width + i);
+    grad[i] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
 }
 
 __global__ void adv_sums_kernel(const float* __restrict__ adv, const int32_t* __restrict__ perm,
@@ -678,12 +728,28 @@ int set_smem(K kernel, size_t bytes, const char* fn) {
 
 }  // namespace
 
+namespace tsb {  // tensor-core path (mlp_tc.cu)
+bool tc_supported(const ts_actor_critic_desc& d);
+int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
+                       const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
+                       const int32_t* perm, int64_t lo, int64_t hi, int64_t global_rows, const float* adv_moments,
+                       float* grad, cudaStream_t st);
+int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
+                      const float* in1, float* out1, int64_t n, cudaStream_t st);
+static bool simt_forced() {
+    static const bool f = [] { const char* e = getenv("TS_B200_FORCE_SIMT"); return e && e[0] == '1'; }();
+    return f;
+}
+}  // namespace tsb
+
 extern "C" int ts_critic_forward(const float* params, const ts_actor_critic_desc* desc,
                                  const float* obs0, float* v_out0, const float* obs1,
                                  float* v_out1, int64_t n, ts_stream_t stream) {
     if (check_desc(desc, "ts_critic_forward")) return 2;
     if (n == 0) return 0;
     TS_REQUIRE(params && obs0 && v_out0 && (!obs1 || v_out1), "ts_critic_forward: null pointer");
+    if (tsb::tc_supported(*desc) && !tsb::simt_forced())
+        return tsb::launch_forward_tc(0, params, *desc, obs0, v_out0, obs1, v_out1, n, tsb::as_stream(stream));
     const size_t smem = smem_bytes(*desc, 0);
     if (set_smem(critic_forward_kernel, smem, "ts_critic_forward")) return 1;
     const int64_t tiles = ((n + kRows - 1) / kRows) * (obs1 ? 2 : 1);
@@ -698,6 +764,8 @@ extern "C" int ts_actor_logp(const float* params, const ts_actor_critic_desc* de
     if (check_desc(desc, "ts_actor_logp")) return 2;
     if (n == 0) return 0;
     TS_REQUIRE(params && obs && act && logp_out, "ts_actor_logp: null pointer");
+    if (tsb::tc_supported(*desc) && !tsb::simt_forced())
+        return tsb::launch_forward_tc(1, params, *desc, obs, logp_out, act, mu_out, n, tsb::as_stream(stream));
     const size_t smem = smem_bytes(*desc, 1);
     if (set_smem(actor_logp_kernel, smem, "ts_actor_logp")) return 1;
     const int64_t tiles = (n + kRows - 1) / kRows;
@@ -710,19 +778,27 @@ extern "C" int ts_ppo_grad(const float* params, const ts_actor_critic_desc* desc
                            const ts_ppo_hparams* hp, const float* obs, const float* act,
                            const float* adv, const float* ret, const float* logp_old,
                            const float* v_s, const int32_t* perm, int64_t lo, int64_t hi,
-                           int64_t global_rows, const float* adv_moments, float* grad,
-                           ts_stream_t stream) {
+                           int64_t global_rows, const float* adv_moments, float* partials,
+                           int32_t* n_partials_out, ts_stream_t stream) {
     if (check_desc(desc, "ts_ppo_grad")) return 2;
     TS_REQUIRE(hp != nullptr, "ts_ppo_grad: null hparams");
     TS_REQUIRE(hi >= lo && global_rows > 0, "ts_ppo_grad: bad row range");
+    if (n_partials_out) *n_partials_out = 0;
     if (hi == lo) return 0;
-    TS_REQUIRE(params && obs && act && adv && ret && logp_old && v_s && grad, "ts_ppo_grad: null pointer");
+    TS_REQUIRE(params && obs && act && adv && ret && logp_old && v_s && partials && n_partials_out, "ts_ppo_grad: null pointer");
+    {
+        const int64_t tiles_ = (hi - lo + kRows - 1) / kRows;
+        *n_partials_out = (int32_t)tsb::imin(tiles_, tsb::num_sms());
+    }
     TS_REQUIRE(!hp->advantage_normalization || adv_moments, "ts_ppo_grad: advantage_normalization needs adv_moments");
+    if (tsb::tc_supported(*desc) && !tsb::simt_forced())   // tcgen05 path (mlp_tc.cu); SIMT covers obs_dim > 32
+        return tsb::launch_ppo_grad_tc(params, *desc, *hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi,
+                                       global_rows, adv_moments, partials, tsb::as_stream(stream));
     const size_t smem = smem_bytes(*desc, 2);
     if (set_smem(ppo_grad_kernel, smem, "ts_ppo_grad")) return 1;
     const int64_t tiles = (hi - lo + kRows - 1) / kRows;
     const unsigned grid = (unsigned)tsb::imin((int64_t)tiles, tsb::num_sms());
-    ppo_grad_kernel<<<grid, kThreads, smem, tsb::as_stream(stream)>>>(params, *desc, *hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi, global_rows, adv_moments, grad);
+    ppo_grad_kernel<<<grid, kThreads, smem, tsb::as_stream(stream)>>>(params, *desc, *hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi, global_rows, adv_moments, partials);
     return tsb::check_launch("ts_ppo_grad");
 }
 
@@ -742,11 +818,24 @@ extern "C" int ts_adv_moments_finalize(const double* sums, int64_t global_rows, 
     return tsb::check_launch("ts_adv_moments_finalize");
 }
 
-extern "C" int ts_clip_adam_step(float* params, float* grad, float* exp_avg, float* exp_avg_sq,
-                                 int64_t* step_count, const ts_actor_critic_desc* desc,
-                                 const ts_ppo_hparams* hp, float* stats_row, ts_stream_t stream) {
+extern "C" int32_t ts_ppo_partial_rows(void) { return tsb::num_sms(); }
+
+extern "C" int ts_grad_reduce(const float* partials, int32_t n_partials, const ts_actor_critic_desc* desc,
+                              float* grad, ts_stream_t stream) {
+    TS_REQUIRE(partials && desc && grad && n_partials >= 0, "ts_grad_reduce: bad arguments");
+    const int64_t width = desc->n_params + TS_PPO_GRAD_EXTRA;
+    grad_reduce_kernel<<<(unsigned)((width + 255) / 256), 256, 0, tsb::as_stream(stream)>>>(partials, n_partials, width, grad);
+    return tsb::check_launch("ts_grad_reduce");
+}
+
+extern "C" int ts_clip_adam_step(float* params, float* grad, const float* partials, int32_t n_partials,
+                                 float* exp_avg, float* exp_avg_sq, int64_t* step_count,
+                                 const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp, float* stats_row,
+                                 ts_stream_t stream) {
     TS_REQUIRE(params && grad && exp_avg && exp_avg_sq && step_count && desc && hp, "ts_clip_adam_step: null pointer");
-    clip_adam_kernel<<<1, 1024, 0, tsb::as_stream(stream)>>>(params, grad, exp_avg, exp_avg_sq, step_count, desc->n_params, *hp, stats_row);
+    const unsigned adam_ctas = (unsigned)((desc->n_params + TS_PPO_GRAD_EXTRA + 1023) / 1024);
+    TS_REQUIRE(adam_ctas <= (unsigned)tsb::num_sms(), "ts_clip_adam_step: parameter vector too large for the single-wave grid barrier");
+    clip_adam_kernel<<<adam_ctas, 1024, 0, tsb::as_stream(stream)>>>(params, grad, partials, n_partials, exp_avg, exp_avg_sq, step_count, desc->n_params, *hp, stats_row);
     return tsb::check_launch("ts_clip_adam_step");
 }
 
@@ -763,7 +852,7 @@ extern "C" int ts_make_permutation(uint64_t seed, int32_t first_epoch, int32_t n
     return tsb::check_launch("ts_make_permutation");
 }
 
-extern "C" int ts_ppo_update(float* params, float* grad, float* exp_avg, float* exp_avg_sq,
+extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, float* exp_avg_sq,
                              int64_t* step_count, const ts_actor_critic_desc* desc,
                              const ts_ppo_hparams* hp, const float* obs, const float* obs_next,
                              const float* act, const double* rew, const uint8_t* terminated,
@@ -774,7 +863,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* exp_avg, float* 
                              double* rms_state, double rms_eps, void* gae_ws, void* adv_tmp,
                              float* stats, ts_stream_t stream) {
     if (check_desc(desc, "ts_ppo_update")) return 2;
-    TS_REQUIRE(hp && bounds && stats && repeat >= 0 && n_minibatch >= 0, "ts_ppo_update: bad arguments");
+    TS_REQUIRE(hp && bounds && stats && partials && grad && repeat >= 0 && n_minibatch >= 0, "ts_ppo_update: bad arguments");
     TS_REQUIRE(!hp->advantage_normalization || adv_tmp, "ts_ppo_update: adv_tmp required");
     double* adv_sums = static_cast<double*>(adv_tmp);
     float* adv_mom = adv_tmp ? reinterpret_cast<float*>(adv_sums + 2) : nullptr;
@@ -792,10 +881,11 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* exp_avg, float* 
                 if (int e = ts_minibatch_adv_sums(adv, pr, lo, hi, adv_sums, stream)) return e;
                 if (int e = ts_adv_moments_finalize(adv_sums, hi - lo, adv_mom, stream)) return e;
             }
+            int32_t n_part = 0;
             if (int e = ts_ppo_grad(params, desc, hp, obs, act, adv, returns, logp_old, v_s, pr, lo, hi,
-                                    hi - lo, adv_mom, grad, stream)) return e;
+                                    hi - lo, adv_mom, partials, &n_part, stream)) return e;
             float* row = stats + ((int64_t)r * n_minibatch + m) * TS_PPO_STATS_STRIDE;
-            if (int e = ts_clip_adam_step(params, grad, exp_avg, exp_avg_sq, step_count, desc, hp, row, stream)) return e;
+            if (int e = ts_clip_adam_step(params, grad, partials, n_part, exp_avg, exp_avg_sq, step_count, desc, hp, row, stream)) return e;
         }
     }
     return 0;

@@ -1,0 +1,659 @@
+// Actor-critic MLP kernels on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as the SIMT kernels in mlp.cu (ts_ppo_grad / ts_critic_forward / ts_actor_logp);
+// reference code replaced: modelfree/ppo.py:157-161,179-211, modelfree/a2c.py:123-126,
+// algorithm_base.py:497.
+//
+// Numerics: every GEMM is an fp32-faithful product built from bf16 tensor-core MMAs with fp32
+// accumulation in TMEM: each operand element x is stored as three bf16 pieces b0 + b1 + b2 = x
+// (24 significant bits) and the six partial products of weight >= 2^-16 are accumulated
+// (umma::gemm_bf16x3).  A single-pass bf16/tf32 MMA would be 6x / 3x cheaper but is ~1e-3 off
+// the reference's fp32 results, which breaks the 1e-5 parity bar on v_s / returns / advantages.
+//
+// Layout: one CTA = one tile of 128 transitions = the 128 TMEM lanes.  Every operand matrix
+// (activations X, H1, H2, gradients, weights) lives in shared memory in the blocked no-swizzle
+// layout of umma.cuh (8-row x 16-byte core matrices), ONE copy per matrix: the same bytes are
+// consumed K-major by the forward / input-gradient GEMMs and MN-major (reduction over the 128
+// rows) by the weight-gradient GEMMs.  Activations never leave the SM between forward and backward:
+//   X -(W1)-> D1 -tanh-> H1 -(W2)-> D2 -tanh-> H2 -(W3)-> D3 -> loss -> dOut
+//   dW3 = H2^T dOut ; dZ2 = (dOut W3) (1-H2^2) [overwrites H2] ; dW2 = dZ2^T H1 ; db2 = dZ2^T 1 ;
+//   dH1 = dZ2 W2 ; dZ1 = dH1 (1-H1^2) [overwrites H1] ; dW1 = dZ1^T X ; db1 = dZ1^T 1
+// Bias gradients come out of the tensor core too (B operand = a 128 x 8 block of ones).
+// MMAs are issued by one thread, completion is signalled through an mbarrier (tcgen05.commit);
+// the 8 warps do the TMEM -> register epilogues (tanh, loss, splits) and the gradient REDs.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "ppo_math.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int H = 64;
+constexpr int kRows = 128;
+constexpr int kThreads = 256;
+constexpr int kMaxAct = 16;
+constexpr int NO = 16;            // padded head width (N of the head GEMM, columns of dOut)
+
+// TMEM column map (fp32 accumulators)
+constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, cDH1 = 192, cDW2 = 256, cDB2 = 320, cDW3 = 352, cDW1 = 384, cDB1 = 448;
+constexpr uint32_t kTmemCols = 512;
+
+// ---- bf16x3 operand matrices in shared memory --------------------------------------------------
+struct Mat {
+    uint32_t base;   // shared address of piece 0
+    uint32_t part;   // bytes between pieces
+    uint32_t RS;     // bytes between 8-row groups (= cols/8 * 128)
+};
+__host__ __device__ inline uint32_t mat_bytes(int rows, int cols) { return (uint32_t)rows * cols * 2u; }
+__device__ __forceinline__ uint32_t moff(uint32_t r, uint32_t c, uint32_t RS) {
+    return (r >> 3) * RS + (c >> 3) * 128u + (r & 7u) * 16u + (c & 7u) * 2u;
+}
+
+struct Split3 { __nv_bfloat16 b0, b1, b2; };
+__device__ __forceinline__ Split3 split3(float x) {
+    Split3 s;
+    s.b0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(s.b0);
+    s.b1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(s.b1);
+    s.b2 = __float2bfloat16_rn(r2);
+    return s;
+}
+__device__ __forceinline__ void store_elem(uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c, float x) {
+    const Split3 s = split3(x);
+    uint8_t* p = sm0 + (m.base + moff(r, c, m.RS));
+    *reinterpret_cast<__nv_bfloat16*>(p) = s.b0;
+    *reinterpret_cast<__nv_bfloat16*>(p + m.part) = s.b1;
+    *reinterpret_cast<__nv_bfloat16*>(p + 2 * m.part) = s.b2;
+}
+// 8 consecutive columns (one 16-byte chunk) of row r
+__device__ __forceinline__ void store_chunk8(uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c0, const float* v) {
+    uint32_t w0[4], w1[4], w2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const Split3 a = split3(v[2 * j]), b = split3(v[2 * j + 1]);
+        w0[j] = (uint32_t)__bfloat16_as_ushort(a.b0) | ((uint32_t)__bfloat16_as_ushort(b.b0) << 16);
+        w1[j] = (uint32_t)__bfloat16_as_ushort(a.b1) | ((uint32_t)__bfloat16_as_ushort(b.b1) << 16);
+        w2[j] = (uint32_t)__bfloat16_as_ushort(a.b2) | ((uint32_t)__bfloat16_as_ushort(b.b2) << 16);
+    }
+    uint8_t* p = sm0 + (m.base + moff(r, c0, m.RS));
+    *reinterpret_cast<uint4*>(p) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    *reinterpret_cast<uint4*>(p + m.part) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    *reinterpret_cast<uint4*>(p + 2 * m.part) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+}
+__device__ __forceinline__ void load_chunk8(const uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c0, float* v) {
+    const uint8_t* p = sm0 + (m.base + moff(r, c0, m.RS));
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint4 b = *reinterpret_cast<const uint4*>(p + m.part);
+    const uint4 c = *reinterpret_cast<const uint4*>(p + 2 * m.part);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, cw[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // bf16 -> f32 is a 16-bit shift
+        v[2 * j] = __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16) + __uint_as_float(cw[j] << 16);
+        v[2 * j + 1] = __uint_as_float(aw[j] & 0xffff0000u) + __uint_as_float(bw[j] & 0xffff0000u) +
+                       __uint_as_float(cw[j] & 0xffff0000u);
+    }
+}
+
+// D[M x N] (+)= A * B^T-like product; operand usage (K-major / MN-major) per flag; issued by 1 thread
+__device__ __forceinline__ void gemm(uint32_t d_tmem, int M, int N, const Mat& A, int a_mn, const Mat& B, int b_mn,
+                                     int K) {
+    const uint32_t a_lbo = a_mn ? A.RS : 128u, a_sbo = a_mn ? 128u : A.RS, a_step = a_mn ? 2u * A.RS : 256u;
+    const uint32_t b_lbo = b_mn ? B.RS : 128u, b_sbo = b_mn ? 128u : B.RS, b_step = b_mn ? 2u * B.RS : 256u;
+    umma::gemm_bf16x3(d_tmem, A.base, A.part, a_lbo, a_sbo, a_step, B.base, B.part, b_lbo, b_sbo, b_step,
+                      umma::idesc_bf16(M, N, a_mn, b_mn), K / 16, false);
+}
+// B = block of ones (single exact piece): D[M x 8] = A^T 1, A used MN-major
+__device__ __forceinline__ void gemm_colsum(uint32_t d_tmem, const Mat& A, uint32_t ones_base, uint32_t ones_RS) {
+    const uint32_t idesc = umma::idesc_bf16(64, 8, 1, 1);
+    uint32_t acc = 0;
+    for (int k = 0; k < kRows / 16; ++k) {
+        const uint64_t bd = umma::smem_desc(ones_base + k * 2u * ones_RS, ones_RS, 128u);
+#pragma unroll
+        for (int p = 2; p >= 0; --p) {
+            const uint64_t ad = umma::smem_desc(A.base + p * A.part + k * 2u * A.RS, A.RS, 128u);
+            umma::mma_bf16(d_tmem, ad, bd, idesc, acc);
+            acc = 1u;
+        }
+    }
+}
+
+struct Smem {   // byte offsets from the dynamic shared memory base (all multiples of 128)
+    int KXP;
+    Mat X, H1, H2, DO, W1, W2, W3;
+    uint32_t ONES, ONES_RS;
+    uint32_t w3f, b1, b2, b3, ls, dof, rowv, red, act;
+    uint32_t total;
+};
+__host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
+    Smem s;
+    s.KXP = (obs_dim + 15) & ~15;
+    uint32_t o = 0;
+    auto mat = [&](Mat& m, int rows, int cols) {
+        m.base = sbase + o; m.part = mat_bytes(rows, cols); m.RS = (uint32_t)(cols / 8) * 128u; o += 3u * m.part;
+    };
+    mat(s.X, kRows, s.KXP);
+    mat(s.H1, kRows, H);
+    mat(s.H2, kRows, H);
+    mat(s.DO, kRows, NO);
+    mat(s.W1, H, s.KXP);
+    mat(s.W2, H, H);
+    mat(s.W3, NO, H);
+    s.ONES = sbase + o; s.ONES_RS = 128u; o += mat_bytes(kRows, 8);
+    s.w3f = o;  o += kMaxAct * H * 4;      // natural fp32 W3 [a][k] for the SIMT K=act GEMM
+    s.b1 = o;   o += H * 4;
+    s.b2 = o;   o += H * 4;
+    s.b3 = o;   o += kMaxAct * 4;
+    s.ls = o;   o += kMaxAct * 4;
+    s.dof = o;  o += kRows * kMaxAct * 4;  // dOut in fp32 [r][a]
+    s.act = o;  o += kRows * kMaxAct * 4;  // actions of the tile
+    s.rowv = o; o += 4 * kRows * 4;        // adv, ret, logp_old, v_s
+    s.red = o;  o += 64 * 4;
+    s.total = o;
+    return s;
+}
+
+struct NetG { int64_t w1, b1, w2, b2, w3, b3, ls; };
+
+// stage one network's weights: bf16x3 blocked copies for the tensor core + fp32 side copies
+__device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const float* __restrict__ params, const NetG& g,
+                              int obs_dim, int out_dim) {
+    const int tid = threadIdx.x;
+    for (int e = tid; e < H * S.KXP; e += kThreads) {
+        const int o = e / S.KXP, k = e - o * S.KXP;
+        store_elem(sm0, S.W1, o, k, k < obs_dim ? __ldg(params + g.w1 + (int64_t)o * obs_dim + k) : 0.0f);
+    }
+    for (int e = tid; e < H * H; e += kThreads) store_elem(sm0, S.W2, e >> 6, e & 63, __ldg(params + g.w2 + e));
+    float* w3f = reinterpret_cast<float*>(sm + S.w3f);
+    for (int e = tid; e < NO * H; e += kThreads) {
+        const int a = e >> 6, k = e & 63;
+        const float w = a < out_dim ? __ldg(params + g.w3 + a * H + k) : 0.0f;
+        store_elem(sm0, S.W3, a, k, w);
+        if (a < kMaxAct) w3f[e] = w;
+    }
+    float* b1 = reinterpret_cast<float*>(sm + S.b1);
+    float* b2 = reinterpret_cast<float*>(sm + S.b2);
+    float* b3 = reinterpret_cast<float*>(sm + S.b3);
+    float* ls = reinterpret_cast<float*>(sm + S.ls);
+    for (int e = tid; e < H; e += kThreads) { b1[e] = __ldg(params + g.b1 + e); b2[e] = __ldg(params + g.b2 + e); }
+    if (tid < kMaxAct) {
+        b3[tid] = tid < out_dim ? __ldg(params + g.b3 + tid) : 0.0f;
+        ls[tid] = (tid < out_dim && g.ls >= 0) ? __ldg(params + g.ls + tid) : 0.0f;
+    }
+}
+
+struct Pipe {   // MMA issue / completion handshake
+    uint64_t* bar;
+    uint32_t phase;
+    // all threads: make smem writes + tcgen05.ld's visible, then thread 0 issues `f` and commits
+    template <class F>
+    __device__ __forceinline__ void run(F&& f) {
+        umma::fence_async_smem();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            umma::fence_after_sync();
+            f();
+            umma::mma_commit(bar);
+        }
+        umma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        umma::fence_after_sync();
+    }
+};
+
+// TMEM (row = 32*(warp&3)+lane, 32 columns starting at col) -> tanh(x + bias) -> bf16x3 rows of OUT
+__device__ __forceinline__ void epi_tanh(uint8_t* sm, uint8_t* sm0, const Mat& OUT, uint32_t tmem, uint32_t col,
+                                         const float* __restrict__ bias) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
+    float v[32];
+    umma::tmem_ld32(tmem + ((32u * (warp & 3)) << 16) + col + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = ppo::tanh_fast(v[j] + bias[c0 + j]);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) store_chunk8(sm0, OUT, r, c0 + j, v + j);
+}
+// TMEM dH -> dZ = dH * (1 - h^2) with h read from (and dZ written back to) ACT
+__device__ __forceinline__ void epi_dtanh_inplace(uint8_t* sm0, const Mat& ACT, uint32_t tmem, uint32_t col) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
+    float v[32];
+    umma::tmem_ld32(tmem + ((32u * (warp & 3)) << 16) + col + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        float h[8];
+        load_chunk8(sm0, ACT, r, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = v[j + i] * (1.0f - h[i] * h[i]);
+        store_chunk8(sm0, ACT, r, c0 + j, h);
+    }
+}
+// dZ2 = (dOut W3) * (1 - H2^2), in place over H2 (K = out_dim is tiny: SIMT)
+__device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, const Smem& S, int out_dim) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
+    const float* dof = reinterpret_cast<const float*>(sm + S.dof) + r * kMaxAct;
+    const float* w3f = reinterpret_cast<const float*>(sm + S.w3f);
+    float dv[kMaxAct];
+#pragma unroll
+    for (int a = 0; a < kMaxAct; ++a) dv[a] = a < out_dim ? dof[a] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        float h[8], acc[8];
+        load_chunk8(sm0, S.H2, r, c0 + j, h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+        for (int a = 0; a < out_dim; ++a) {
+            const float4 wa = *reinterpret_cast<const float4*>(w3f + a * H + c0 + j);
+            const float4 wb = *reinterpret_cast<const float4*>(w3f + a * H + c0 + j + 4);
+            acc[0] = fmaf(dv[a], wa.x, acc[0]); acc[1] = fmaf(dv[a], wa.y, acc[1]);
+            acc[2] = fmaf(dv[a], wa.z, acc[2]); acc[3] = fmaf(dv[a], wa.w, acc[3]);
+            acc[4] = fmaf(dv[a], wb.x, acc[4]); acc[5] = fmaf(dv[a], wb.y, acc[5]);
+            acc[6] = fmaf(dv[a], wb.z, acc[6]); acc[7] = fmaf(dv[a], wb.w, acc[7]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = acc[i] * (1.0f - h[i] * h[i]);
+        store_chunk8(sm0, S.H2, r, c0 + j, h);
+    }
+}
+// write one row of dOut: fp32 side copy + bf16x3 operand (columns >= out_dim are zero)
+__device__ __forceinline__ void write_dout_row(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t r, const float* dv) {
+    float* dof = reinterpret_cast<float*>(sm + S.dof) + r * kMaxAct;
+#pragma unroll
+    for (int a = 0; a < kMaxAct; ++a) dof[a] = dv[a];
+    store_chunk8(sm0, S.DO, r, 0, dv);
+    store_chunk8(sm0, S.DO, r, 8, dv + 8);
+}
+
+// weight-gradient accumulators (M = 64: row o = 16*q + lane for lane < 16) -> RED into the flat gradient
+__device__ __forceinline__ void red_rows(uint32_t tmem, uint32_t col, int ncols, float* __restrict__ grad, int64_t base,
+                                         int64_t row_stride, int valid_cols) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2;
+    // the two warps of a sub-partition split the column range in 8-column slabs
+    for (int c0 = 8 * half; c0 < ncols; c0 += 16) {
+        float v[8];
+        umma::tmem_ld8(tmem + ((32u * q) << 16) + col + c0, v);
+        if (lane < 16) {
+            const int o = 16 * q + lane;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c0 + j < valid_cols) atomicAdd(grad + base + (int64_t)o * row_stride + c0 + j, v[j]);
+        }
+    }
+}
+// transposed variant for dW3^T [k][a] -> grad W3[a][k]
+__device__ __forceinline__ void red_w3(uint32_t tmem, uint32_t col, float* __restrict__ grad, int64_t base, int out_dim) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2;
+    float v[8];
+    umma::tmem_ld8(tmem + ((32u * q) << 16) + col + 8 * half, v);
+    if (lane < 16) {
+        const int k = 16 * q + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int a = 8 * half + j;
+            if (a < out_dim) atomicAdd(grad + base + (int64_t)a * H + k, v[j]);
+        }
+    }
+}
+
+// forward of one trunk: X -> H1 -> H2 -> head accumulator D3 (TMEM)
+__device__ __forceinline__ void trunk_forward(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, Pipe& pipe) {
+    pipe.run([&] { gemm(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
+    epi_tanh(sm, sm0, S.H1, tmem, cD1, reinterpret_cast<const float*>(sm + S.b1));
+    pipe.run([&] { gemm(tmem + cD2, 128, H, S.H1, 0, S.W2, 0, H); });
+    epi_tanh(sm, sm0, S.H2, tmem, cD2, reinterpret_cast<const float*>(sm + S.b2));
+    pipe.run([&] { gemm(tmem + cD3, 128, NO, S.H2, 0, S.W3, 0, H); });
+}
+
+// backward of one trunk given dOut (S.DO / dof); REDs all weight and bias gradients of the net
+__device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, Pipe& pipe,
+                                               const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad) {
+    pipe.run([&] { gemm(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1, kRows); });          // dW3^T = H2^T dOut
+    epi_head_input_grad(sm, sm0, S, out_dim);                                         // H2 := dZ2
+    pipe.run([&] {
+        gemm(tmem + cDW2, 64, H, S.H2, 1, S.H1, 1, kRows);                            // dW2 = dZ2^T H1
+        gemm_colsum(tmem + cDB2, S.H2, S.ONES, S.ONES_RS);                            // db2 = dZ2^T 1
+        gemm(tmem + cDH1, 128, H, S.H2, 0, S.W2, 1, H);                               // dH1 = dZ2 W2
+    });
+    epi_dtanh_inplace(sm0, S.H1, tmem, cDH1);                                         // H1 := dZ1
+    pipe.run([&] {
+        gemm(tmem + cDW1, 64, S.KXP, S.H1, 1, S.X, 1, kRows);                         // dW1 = dZ1^T X
+        gemm_colsum(tmem + cDB1, S.H1, S.ONES, S.ONES_RS);                            // db1 = dZ1^T 1
+    });
+    red_w3(tmem, cDW3, grad, g.w3, out_dim);
+    red_rows(tmem, cDW2, H, grad, g.w2, H, H);
+    red_rows(tmem, cDB2, 8, grad, g.b2, 1, 1);
+    red_rows(tmem, cDW1, S.KXP, grad, g.w1, obs_dim, obs_dim);
+    red_rows(tmem, cDB1, 8, grad, g.b1, 1, 1);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
+    const float* __restrict__ params, const ts_actor_critic_desc d, const ts_ppo_hparams hp,
+    const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ adv,
+    const float* __restrict__ ret, const float* __restrict__ logp_old, const float* __restrict__ v_s,
+    const int32_t* __restrict__ perm, int64_t lo, int64_t hi, int64_t global_rows,
+    const float* __restrict__ adv_moments, float* __restrict__ partials) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // this CTA's private partial-gradient row: no cross-CTA atomics, folded by clip_adam_kernel
+    float* __restrict__ grad = partials + (size_t)blockIdx.x * (size_t)(d.n_params + TS_PPO_GRAD_EXTRA);
+    for (int64_t i = tid; i < d.n_params + TS_PPO_GRAD_EXTRA; i += kThreads) grad[i] = 0.0f;
+    const uint32_t sbase = umma::smem_u32(sm);
+    uint8_t* sm0 = sm - sbase;     // so that (sm0 + shared_address) is the generic pointer
+    const Smem S = make_smem(d.obs_dim, sbase);
+    const int A = d.act_dim;
+    const ppo::Scalars sc = ppo::make_scalars(hp, global_rows, adv_moments);
+    const NetG ga{d.a_w1, d.a_b1, d.a_w2, d.a_b2, d.a_w3, d.a_b3, d.a_logstd};
+    const NetG gc{d.c_w1, d.c_b1, d.c_w2, d.c_b2, d.c_w3, d.c_b3, -1};
+
+    if (warp == 0) umma::tmem_alloc(&s_tmem, kTmemCols);
+    if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
+    {   // block of ones (bf16 1.0 = 0x3F80), blocked layout with 1 chunk per row
+        uint32_t* ones = reinterpret_cast<uint32_t*>(sm0 + S.ONES);
+        for (int e = tid; e < kRows * 8 / 2; e += kThreads) ones[e] = 0x3F803F80u;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    Pipe pipe{&s_bar, 0u};
+    float* rowv = reinterpret_cast<float*>(sm + S.rowv);
+    float* red = reinterpret_cast<float*>(sm + S.red);
+    float* actt = reinterpret_cast<float*>(sm + S.act);
+
+    const int64_t tiles = (hi - lo + kRows - 1) / kRows;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t pos0 = lo + t * kRows;
+        const int nrows = (int)tsb::imin((int64_t)kRows, hi - pos0);
+        // ---- tile inputs -----------------------------------------------------------------------
+        for (int e = tid; e < kRows * S.KXP; e += kThreads) {
+            const int r = e / S.KXP, k = e - r * S.KXP;
+            float x = 0.0f;
+            if (r < nrows && k < d.obs_dim) {
+                const int64_t row = perm ? (int64_t)perm[pos0 + r] : pos0 + r;
+                x = __ldg(obs + row * d.obs_dim + k);
+            }
+            store_elem(sm0, S.X, r, k, x);
+        }
+        for (int e = tid; e < kRows * kMaxAct; e += kThreads) {
+            const int r = e / kMaxAct, a = e - r * kMaxAct;
+            float x = 0.0f;
+            if (r < nrows && a < A) {
+                const int64_t row = perm ? (int64_t)perm[pos0 + r] : pos0 + r;
+                x = __ldg(act + row * A + a);
+            }
+            actt[e] = x;
+        }
+        if (tid < kRows) {
+            float a_ = 0.f, r_ = 0.f, l_ = 0.f, v_ = 0.f;
+            if (tid < nrows) {
+                const int64_t row = perm ? (int64_t)perm[pos0 + tid] : pos0 + tid;
+                a_ = __ldg(adv + row); r_ = __ldg(ret + row); l_ = __ldg(logp_old + row); v_ = __ldg(v_s + row);
+            }
+            rowv[tid] = a_; rowv[kRows + tid] = r_; rowv[2 * kRows + tid] = l_; rowv[3 * kRows + tid] = v_;
+        }
+        if (tid < 64) red[tid] = 0.0f;
+
+        // ================= critic ================================================================
+        stage_weights(sm, sm0, S, params, gc, d.obs_dim, 1);
+        trunk_forward(sm, sm0, S, tmem, pipe);
+        float vf_row = 0.0f;
+        if (tid < kRows) {
+            float v16[16], dv[kMaxAct];
+            umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
+#pragma unroll
+            for (int a = 0; a < kMaxAct; ++a) dv[a] = 0.0f;
+            if (tid < nrows) {
+                const float value = v16[0] + reinterpret_cast<const float*>(sm + S.b3)[0];
+                ppo::critic_row(sc, value, rowv[kRows + tid], rowv[3 * kRows + tid], vf_row, dv[0]);
+            }
+            write_dout_row(sm, sm0, S, tid, dv);
+            const float sdv = warp_sum(dv[0]);
+            if (lane == 0) atomicAdd(red + 0, sdv);            // db3 (critic)
+        }
+        trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad);
+        __syncthreads();
+        if (tid == 0) { atomicAdd(grad + gc.b3, red[0]); red[0] = 0.0f; }
+
+        // ================= actor =================================================================
+        stage_weights(sm, sm0, S, params, ga, d.obs_dim, A);
+        trunk_forward(sm, sm0, S, tmem, pipe);
+        float clip_row = 0.0f;
+        if (tid < kRows) {
+            const int r = tid;
+            float v16[16], dv[kMaxAct], dls[kMaxAct];
+            umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
+            const float* b3 = reinterpret_cast<const float*>(sm + S.b3);
+            const float* ls = reinterpret_cast<const float*>(sm + S.ls);
+            float lp = 0.0f;
+            float sig[kMaxAct], diff[kMaxAct];
+#pragma unroll
+            for (int a = 0; a < kMaxAct; ++a) {
+                sig[a] = 1.0f; diff[a] = 0.0f;
+                if (a < A) {
+                    sig[a] = expf(ls[a]);
+                    const float mu = v16[a] + b3[a];
+                    const float x = actt[r * kMaxAct + a];
+                    diff[a] = x - mu;
+                    lp += ppo::normal_logp_term(x, mu, sig[a]);
+                }
+            }
+            float gl = 0.0f;
+            if (r < nrows) ppo::actor_row(sc, lp, rowv[2 * kRows + r], rowv[r], clip_row, gl);
+#pragma unroll
+            for (int a = 0; a < kMaxAct; ++a) {
+                const float var = sig[a] * sig[a];
+                dv[a] = a < A ? gl * diff[a] / var : 0.0f;                       // d/d mu
+                dls[a] = a < A ? gl * (diff[a] * diff[a] / var - 1.0f) : 0.0f;  // d/d logstd
+            }
+            write_dout_row(sm, sm0, S, r, dv);
+            // column sums over the 32 rows of this warp: db3[a] and dlogstd[a]
+#pragma unroll
+            for (int a = 0; a < kMaxAct; ++a) {
+                if (a < A) {
+                    const float s1 = warp_sum(dv[a]), s2 = warp_sum(dls[a]);
+                    if (lane == 0) { atomicAdd(red + 16 + a, s1); atomicAdd(red + 32 + a, s2); }
+                }
+            }
+        }
+        trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad);
+
+        // ================= loss sums + small gradients ===========================================
+        const float s_clip = warp_sum(tid < kRows ? clip_row : 0.0f);
+        const float s_vf = warp_sum(tid < kRows ? vf_row : 0.0f);
+        if (lane == 0 && tid < kRows) { atomicAdd(red + 1, s_clip); atomicAdd(red + 2, s_vf); }
+        __syncthreads();
+        if (tid < A) {
+            atomicAdd(grad + ga.b3 + tid, red[16 + tid]);
+            atomicAdd(grad + ga.ls + tid, red[32 + tid] - sc.ent_coef * sc.inv_b * (float)nrows);
+        }
+        if (tid == 0) {
+            const float* ls = reinterpret_cast<const float*>(sm + S.ls);
+            float ent = 0.0f;
+            for (int a = 0; a < A; ++a) ent += 1.4189385332046727f + logf(expf(ls[a]));
+            float* ex = grad + d.n_params;
+            atomicAdd(ex + 0, red[1]);
+            atomicAdd(ex + 1, red[2]);
+            atomicAdd(ex + 2, ent * (float)nrows);
+            atomicAdd(ex + 3, (float)nrows);
+        }
+        __syncthreads();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+
+// ---- forward-only kernels (value pass / log-prob pass), persistent over 128-row tiles -----------
+struct SmemF {
+    int KXP;
+    Mat X, H1, W1, W2;
+    uint32_t w3f, b1, b2, b3, ls, part;
+    uint32_t total;
+};
+__host__ __device__ inline SmemF make_smem_f(int obs_dim, uint32_t sbase) {
+    SmemF s;
+    s.KXP = (obs_dim + 15) & ~15;
+    uint32_t o = 0;
+    auto mat = [&](Mat& m, int rows, int cols) {
+        m.base = sbase + o; m.part = mat_bytes(rows, cols); m.RS = (uint32_t)(cols / 8) * 128u; o += 3u * m.part;
+    };
+    mat(s.X, kRows, s.KXP);
+    mat(s.H1, kRows, H);
+    mat(s.W1, H, s.KXP);
+    mat(s.W2, H, H);
+    s.w3f = o;  o += kMaxAct * H * 4;
+    s.b1 = o;   o += H * 4;
+    s.b2 = o;   o += H * 4;
+    s.b3 = o;   o += kMaxAct * 4;
+    s.ls = o;   o += kMaxAct * 4;
+    s.part = o; o += 2 * kRows * kMaxAct * 4;   // head partial sums of the two column halves
+    s.total = o;
+    return s;
+}
+
+// MODE 0: out0[r] = critic(in0[r]) and (if in1) out1[r] = critic(in1[r])      (a2c.py:123-126)
+// MODE 1: out0[r] = log N(in1[r] | mu(in0[r]), exp(logstd)), out1 = mu (nullable)   (ppo.py:157-161)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
+    const float* __restrict__ params, const ts_actor_critic_desc d, const float* __restrict__ in0,
+    float* __restrict__ out0, const float* __restrict__ in1, float* __restrict__ out1, int64_t n) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sbase = umma::smem_u32(sm);
+    uint8_t* sm0 = sm - sbase;
+    const SmemF S = make_smem_f(d.obs_dim, sbase);
+    const int out_dim = MODE == 0 ? 1 : d.act_dim;
+    const NetG g = MODE == 0 ? NetG{d.c_w1, d.c_b1, d.c_w2, d.c_b2, d.c_w3, d.c_b3, -1}
+                             : NetG{d.a_w1, d.a_b1, d.a_w2, d.a_b2, d.a_w3, d.a_b3, d.a_logstd};
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 128);
+    if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
+    // weights: W1, W2 as tensor-core operands; head weights / biases as fp32
+    for (int e = tid; e < H * S.KXP; e += kThreads) {
+        const int o = e / S.KXP, k = e - o * S.KXP;
+        store_elem(sm0, S.W1, o, k, k < d.obs_dim ? __ldg(params + g.w1 + (int64_t)o * d.obs_dim + k) : 0.0f);
+    }
+    for (int e = tid; e < H * H; e += kThreads) store_elem(sm0, S.W2, e >> 6, e & 63, __ldg(params + g.w2 + e));
+    float* w3f = reinterpret_cast<float*>(sm + S.w3f);
+    float* b1 = reinterpret_cast<float*>(sm + S.b1);
+    float* b2 = reinterpret_cast<float*>(sm + S.b2);
+    float* b3 = reinterpret_cast<float*>(sm + S.b3);
+    float* ls = reinterpret_cast<float*>(sm + S.ls);
+    float* part = reinterpret_cast<float*>(sm + S.part);
+    for (int e = tid; e < kMaxAct * H; e += kThreads) w3f[e] = (e >> 6) < out_dim ? __ldg(params + g.w3 + e) : 0.0f;
+    for (int e = tid; e < H; e += kThreads) { b1[e] = __ldg(params + g.b1 + e); b2[e] = __ldg(params + g.b2 + e); }
+    if (tid < kMaxAct) {
+        b3[tid] = tid < out_dim ? __ldg(params + g.b3 + tid) : 0.0f;
+        ls[tid] = (MODE == 1 && tid < out_dim) ? __ldg(params + g.ls + tid) : 0.0f;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    Pipe pipe{&s_bar, 0u};
+
+    const int64_t tiles_per = (n + kRows - 1) / kRows;
+    const int64_t tiles = tiles_per * ((MODE == 0 && in1) ? 2 : 1);
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const bool second = t >= tiles_per;
+        const int64_t row0 = (second ? t - tiles_per : t) * kRows;
+        const int nrows = (int)tsb::imin((int64_t)kRows, n - row0);
+        const float* src = (MODE == 0 && second) ? in1 : in0;
+        // the tile's rows are contiguous in memory: coalesced read, scattered bf16x3 store
+        for (int e = tid; e < kRows * S.KXP; e += kThreads) {
+            const int r = e / S.KXP, k = e - r * S.KXP;
+            store_elem(sm0, S.X, r, k, (r < nrows && k < d.obs_dim) ? __ldg(src + (row0 + r) * d.obs_dim + k) : 0.0f);
+        }
+        pipe.run([&] { gemm(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
+        epi_tanh(sm, sm0, S.H1, tmem, cD1, b1);
+        pipe.run([&] { gemm(tmem + cD2, 128, H, S.H1, 0, S.W2, 0, H); });
+        {   // h2 = tanh(D2 + b2) stays in registers; head = h2 . W3^T (K = 64 split over the two column halves)
+            const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
+            float v[32];
+            umma::tmem_ld32(tmem + ((32u * (warp & 3)) << 16) + cD2 + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ppo::tanh_fast(v[j] + b2[c0 + j]);
+            for (int a = 0; a < out_dim; ++a) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc = fmaf(v[j], w3f[a * H + c0 + j], acc);
+                part[((warp >> 2) * kRows + r) * kMaxAct + a] = acc;
+            }
+        }
+        __syncthreads();
+        if (tid < nrows) {
+            const int r = tid;
+            if (MODE == 0) {
+                (second ? out1 : out0)[row0 + r] = part[r * kMaxAct] + part[(kRows + r) * kMaxAct] + b3[0];
+            } else {
+                float lp = 0.0f;
+                for (int a = 0; a < out_dim; ++a) {
+                    const float mu = part[r * kMaxAct + a] + part[(kRows + r) * kMaxAct + a] + b3[a];
+                    lp += ppo::normal_logp_term(__ldg(in1 + (row0 + r) * out_dim + a), mu, expf(ls[a]));
+                    if (out1) out1[(row0 + r) * out_dim + a] = mu;
+                }
+                out0[row0 + r] = lp;
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+
+}  // namespace
+
+namespace tsb {
+bool tc_supported(const ts_actor_critic_desc& d) {
+    return d.hidden == H && d.obs_dim >= 1 && d.obs_dim <= 32 && d.act_dim >= 1 && d.act_dim <= kMaxAct;
+}
+
+int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
+                       const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
+                       const int32_t* perm, int64_t lo, int64_t hi, int64_t global_rows, const float* adv_moments,
+                       float* grad, cudaStream_t st) {
+    const size_t smem = make_smem(d.obs_dim, 0).total;
+    static size_t configured = 0;
+    if (smem > configured) {
+        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int64_t tiles = (hi - lo + kRows - 1) / kRows;
+    const unsigned grid = (unsigned)imin(tiles, num_sms());
+    ppo_grad_tc_kernel<<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi,
+                                                     global_rows, adv_moments, grad);
+    return check_launch("ts_ppo_grad(tc)");
+}
+
+int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
+                      const float* in1, float* out1, int64_t n, cudaStream_t st) {
+    const size_t smem = make_smem_f(d.obs_dim, 0).total;
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[mode]) {
+        if (mode == 0) TS_CUDA(cudaFuncSetAttribute(forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else TS_CUDA(cudaFuncSetAttribute(forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[mode] = smem;
+    }
+    const int64_t tiles = ((n + kRows - 1) / kRows) * ((mode == 0 && in1) ? 2 : 1);
+    const unsigned grid = (unsigned)imin(tiles, num_sms());
+    if (mode == 0) forward_tc_kernel<0><<<grid, kThreads, smem, st>>>(params, d, in0, out0, in1, out1, n);
+    else forward_tc_kernel<1><<<grid, kThreads, smem, st>>>(params, d, in0, out0, in1, out1, n);
+    return check_launch(mode == 0 ? "ts_critic_forward(tc)" : "ts_actor_logp(tc)");
+}
+}  // namespace tsb
