@@ -216,6 +216,7 @@ def main() -> None:
 
     from tianshou_b200 import _cabi
     from tianshou_b200._cabi import call, ptr, stream_ptr
+    from tianshou_b200 import ops
     from tianshou_b200.synthetic import build_mujoco_ppo
     from tianshou_b200.utils import policy_within_training_step
 
@@ -300,23 +301,41 @@ def main() -> None:
     perm = torch.randperm(N, device=dev).to(torch.int32)
     reps = 40
     rows = min(BATCH_SIZE, N)
-    grad_events = []
+    grad_events, adam_events = [], []
     n_part = C.c_int32(0)
+    scratch_stats = torch.zeros(8, dtype=torch.float32, device=dev)
+    # save optimiser state: the timing loop below takes real Adam steps
+    saved = [t.clone() for t in (f.flat, f.exp_avg, f.exp_avg_sq, f.step)]
     for i in range(reps + 5):
         lo = (i * rows) % max(1, N - rows + 1)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s, m, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         s.record()
         call("ts_ppo_grad", ptr(f.flat), C.byref(algo._desc), C.byref(hp), ptr(b.obs), ptr(b.act), ptr(b.adv),
              ptr(b.returns), ptr(b.logp_old), ptr(b.v_s), ptr(perm), lo, lo + rows, rows, None, ptr(f.partials),
              C.byref(n_part), stream_ptr(dev))
+        m.record()
+        call("ts_clip_adam_step", ptr(f.flat), ptr(f.grad), ptr(f.partials), n_part.value, ptr(f.exp_avg),
+             ptr(f.exp_avg_sq), ptr(f.step), C.byref(algo._desc), C.byref(hp), ptr(scratch_stats), stream_ptr(dev))
         e.record()
         if i >= 5:
-            grad_events.append((s, e))
+            grad_events.append((s, m))
+            adam_events.append((m, e))
     torch.cuda.synchronize()
-    f.grad.zero_()
+    for dst, src in zip((f.flat, f.exp_avg, f.exp_avg_sq, f.step), saved):
+        dst.copy_(src)
     grad_ms = sum(s.elapsed_time(e) for s, e in grad_events) / len(grad_events)
+    adam_ms = sum(s.elapsed_time(e) for s, e in adam_events) / len(adam_events)
+    fwd_events = []
+    for i in range(8):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.critic_forward(f.flat, algo._desc, b.obs, b.obs_next, out=b.v_s, out2=algo._buf("v_next", N, torch.float32))
+        e.record()
+        if i >= 2:
+            fwd_events.append((s, e))
+    torch.cuda.synchronize()
+    fwd_ms = sum(s.elapsed_time(e) for s, e in fwd_events) / len(fwd_events)
     # GAE scan alone (HBM-bound kernel)
-    from tianshou_b200 import ops
     gae_events = []
     for i in range(25):
         flush.zero_()
@@ -369,6 +388,8 @@ def main() -> None:
         "roofline_gae": {"kernel": "gae_scan_kernel", "bound": "hbm", "achieved": gae_bytes / (gae_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gae_bytes / (gae_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "algorithmic_bytes_per_launch": gae_bytes, "launch_ms": gae_ms, "peak_source": peak_src},
+        "kernel_ms": {"ppo_grad": grad_ms, "clip_adam(reduce+norm+adam)": adam_ms, "critic_forward(v_s,v_s_)": fwd_ms,
+                      "gae_scan": gae_ms},
         "flops_per_transition": FLOP_PER_TRANSITION,
         "update_tflops": FLOP_PER_TRANSITION * total_transitions * K / (ms_dev / 1e3) / 1e12,
         "clocks": clocks,

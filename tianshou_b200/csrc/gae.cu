@@ -277,22 +277,23 @@ __global__ void __launch_bounds__(kThreads) gae_scan_kernel(const GaeParams p) {
     const bool want_moments = (p.rms != nullptr) || (p.batch_moments != nullptr);
     double g = eB + eA * s_carry;  // adv just right of this thread's items
     double advv[kItems], retv[kItems];
-    double mn = 0.0, mm = 0.0, mM = 0.0;
-    const double inv_scale = 1.0 / scale;
-    (void)inv_scale;
+    // moments of the un-scaled returns: pivot-shifted sums (one division per thread, not per item)
+    double mn = 0.0, pivot = 0.0, s1 = 0.0, s2 = 0.0;
+    const bool scaled = (p.rms != nullptr);
 #pragma unroll
     for (int j = kItems - 1; j >= 0; --j) {
         g = d[j] + a[j] * g;
         advv[j] = g;
         const double r = g + vs[j];  // un-scaled return (algorithm_base.py:717)
-        retv[j] = r / scale;          // a2c.py:146
+        retv[j] = scaled ? r / scale : r;   // a2c.py:146
         if (want_moments && base + j < p.n) {
-            mn += 1.0;
-            const double dl = r - mm;
-            mm += dl / mn;
-            mM += dl * (r - mm);
+            if (mn == 0.0) pivot = r;
+            const double dl = r - pivot;
+            mn += 1.0; s1 += dl; s2 += dl * dl;
         }
     }
+    double mm = 0.0, mM = 0.0;
+    if (mn > 0.0) { mm = pivot + s1 / mn; mM = s2 - s1 * s1 / mn; if (mM < 0.0) mM = 0.0; }
     if (p.vec_ok && base + kItems <= p.n) {
         store8<TO>(static_cast<TO*>(p.adv_out), base, advv);
         store8<TO>(static_cast<TO*>(p.ret_out), base, retv);

@@ -539,44 +539,53 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
 __device__ unsigned int g_adam_arrive = 0, g_adam_depart = 0;
 __device__ double g_adam_ss = 0.0;
 
-// gradient fold + clip_grad_norm_ + Adam in one launch, ~11 co-resident CTAs of 1024 threads, one
-// parameter per thread: (0) fold the per-CTA partial rows of this parameter in a fixed order
-// (coalesced across threads, L2 resident), (1) block sum of squares -> one f64 atomic per CTA,
-// (2) grid barrier, (3) norm, clip coefficient, Adam update of the own element.
-__global__ void __launch_bounds__(1024) clip_adam_kernel(
+// gradient fold + clip_grad_norm_ + Adam in one launch.  CTA = 256 parameters x 4 partial groups
+// (1024 threads), ~44 co-resident CTAs: (0) thread (e, q) folds the partial rows p = q (mod 4) of
+// its parameter (coalesced across e, L2 resident), the 4 groups are combined through shared memory
+// in a fixed order; (1) block sum of squares -> one f64 atomic per CTA; (2) grid barrier; (3) norm,
+// clip coefficient, Adam update of the CTA's 256 parameters.
+constexpr int kAdamElems = 256, kAdamGroups = 4;
+__global__ void __launch_bounds__(kAdamElems * kAdamGroups) clip_adam_kernel(
     float* __restrict__ params, float* __restrict__ grad, const float* __restrict__ partials, int n_partials,
     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t* __restrict__ step_count,
     int64_t n_params, const ts_ppo_hparams hp, float* __restrict__ stats_row) {
-    __shared__ double s_red[32];
+    __shared__ double s_red[8];
+    __shared__ float s_part[kAdamGroups][kAdamElems];
     __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, e = tid & (kAdamElems - 1), q = tid >> 8;
     const int64_t step = *step_count + 1;
     const int64_t width = n_params + TS_PPO_GRAD_EXTRA;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int64_t i = (int64_t)blockIdx.x * kAdamElems + e;
     float g = 0.0f;
-    if (i < width) {
-        if (partials) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int p = 0;
-            for (; p + 8 <= n_partials; p += 8) {
+    if (partials) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (i < width) {
+            int p = q;
+            for (; p + 7 * kAdamGroups < n_partials; p += 8 * kAdamGroups) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc[u] += __ldcg(partials + (int64_t)(p + u) * width + i);
+                for (int u = 0; u < 8; ++u) acc[u] += __ldcg(partials + (int64_t)(p + u * kAdamGroups) * width + i);
             }
-            for (; p < n_partials; ++p) acc[0] += __ldcg(partials + (int64_t)p * width + i);
-            g = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-            if (i >= n_params) grad[i] = g;          // loss sums, read by CTA 0 after the barrier
-        } else {
-            g = __ldcg(grad + i);
+            for (; p < n_partials; p += kAdamGroups) acc[0] += __ldcg(partials + (int64_t)p * width + i);
         }
+        s_part[q][e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        __syncthreads();
+        if (q == 0) {
+            g = (s_part[0][e] + s_part[1][e]) + (s_part[2][e] + s_part[3][e]);
+            if (i >= n_params && i < width) grad[i] = g;   // loss sums, read by CTA 0 after the barrier
+        }
+    } else if (q == 0 && i < width) {
+        g = __ldcg(grad + i);
     }
-    double ss = (i < n_params) ? (double)g * (double)g : 0.0;
+    double ss = (q == 0 && i < n_params) ? (double)g * (double)g : 0.0;
+    if (tid < kAdamElems) {   // warps 0..7 hold the q == 0 threads
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ss += tsb::shfl_xor_f64(ss, off);
-    if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+        for (int off = 16; off > 0; off >>= 1) ss += tsb::shfl_xor_f64(ss, off);
+        if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+    }
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+        for (int w = 0; w < kAdamElems / 32; ++w) t += s_red[w];
         atomicAdd(&g_adam_ss, t);
         __threadfence();
         atomicAdd(&g_adam_arrive, 1u);
@@ -598,7 +607,7 @@ __global__ void __launch_bounds__(1024) clip_adam_kernel(
     const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
     const float w1 = (float)(1.0 - hp.beta1), w2 = (float)(1.0 - hp.beta2);
     const float beta2 = (float)hp.beta2, adam_eps = (float)hp.adam_eps, wd = (float)hp.weight_decay;
-    if (i < n_params) {
+    if (q == 0 && i < n_params) {
         g *= coef;
         float p = params[i];
         if (wd != 0.0f) g = fmaf(wd, p, g);
@@ -736,6 +745,11 @@ int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const
                        float* grad, cudaStream_t st);
 int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
                       const float* in1, float* out1, int64_t n, cudaStream_t st);
+int launch_ppo_step_tc(float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
+                       const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
+                       const int32_t* perm, int64_t lo, int64_t hi, const float* adv_moments, float* partials,
+                       float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count, float* stats_row,
+                       cudaStream_t st);
 static bool simt_forced() {
     static const bool f = [] { const char* e = getenv("TS_B200_FORCE_SIMT"); return e && e[0] == '1'; }();
     return f;
@@ -833,9 +847,9 @@ extern "C" int ts_clip_adam_step(float* params, float* grad, const float* partia
                                  const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp, float* stats_row,
                                  ts_stream_t stream) {
     TS_REQUIRE(params && grad && exp_avg && exp_avg_sq && step_count && desc && hp, "ts_clip_adam_step: null pointer");
-    const unsigned adam_ctas = (unsigned)((desc->n_params + TS_PPO_GRAD_EXTRA + 1023) / 1024);
+    const unsigned adam_ctas = (unsigned)((desc->n_params + TS_PPO_GRAD_EXTRA + kAdamElems - 1) / kAdamElems);
     TS_REQUIRE(adam_ctas <= (unsigned)tsb::num_sms(), "ts_clip_adam_step: parameter vector too large for the single-wave grid barrier");
-    clip_adam_kernel<<<adam_ctas, 1024, 0, tsb::as_stream(stream)>>>(params, grad, partials, n_partials, exp_avg, exp_avg_sq, step_count, desc->n_params, *hp, stats_row);
+    clip_adam_kernel<<<adam_ctas, kAdamElems * kAdamGroups, 0, tsb::as_stream(stream)>>>(params, grad, partials, n_partials, exp_avg, exp_avg_sq, step_count, desc->n_params, *hp, stats_row);
     return tsb::check_launch("ts_clip_adam_step");
 }
 
@@ -865,6 +879,8 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
     if (check_desc(desc, "ts_ppo_update")) return 2;
     TS_REQUIRE(hp && bounds && stats && partials && grad && repeat >= 0 && n_minibatch >= 0, "ts_ppo_update: bad arguments");
     TS_REQUIRE(!hp->advantage_normalization || adv_tmp, "ts_ppo_update: adv_tmp required");
+    static const bool no_fuse = [] { const char* e = getenv("TS_B200_NO_FUSED_STEP"); return e && e[0] == '1'; }();
+    const bool fused = tsb::tc_supported(*desc) && !tsb::simt_forced() && !no_fuse;
     double* adv_sums = static_cast<double*>(adv_tmp);
     float* adv_mom = adv_tmp ? reinterpret_cast<float*>(adv_sums + 2) : nullptr;
     for (int r = 0; r < repeat; ++r) {
@@ -881,10 +897,16 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
                 if (int e = ts_minibatch_adv_sums(adv, pr, lo, hi, adv_sums, stream)) return e;
                 if (int e = ts_adv_moments_finalize(adv_sums, hi - lo, adv_mom, stream)) return e;
             }
+            float* row = stats + ((int64_t)r * n_minibatch + m) * TS_PPO_STATS_STRIDE;
+            if (fused) {   // one launch per optimiser step
+                if (int e = tsb::launch_ppo_step_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo, hi,
+                                                    adv_mom, partials, grad, exp_avg, exp_avg_sq, step_count, row,
+                                                    tsb::as_stream(stream))) return e;
+                continue;
+            }
             int32_t n_part = 0;
             if (int e = ts_ppo_grad(params, desc, hp, obs, act, adv, returns, logp_old, v_s, pr, lo, hi,
                                     hi - lo, adv_mom, partials, &n_part, stream)) return e;
-            float* row = stats + ((int64_t)r * n_minibatch + m) * TS_PPO_STATS_STRIDE;
             if (int e = ts_clip_adam_step(params, grad, partials, n_part, exp_avg, exp_avg_sq, step_count, desc, hp, row, stream)) return e;
         }
     }

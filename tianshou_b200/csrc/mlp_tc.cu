@@ -32,7 +32,8 @@ namespace {
 
 constexpr int H = 64;
 constexpr int kRows = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;        // 16 warps: 4 per TMEM sub-partition, 16 accumulator columns per thread
+constexpr int kCols = 16;            // columns of a 64-wide layer owned by one thread in the epilogues
 constexpr int kMaxAct = 16;
 constexpr int NO = 16;            // padded head width (N of the head GEMM, columns of dOut)
 
@@ -51,73 +52,62 @@ __device__ __forceinline__ uint32_t moff(uint32_t r, uint32_t c, uint32_t RS) {
     return (r >> 3) * RS + (c >> 3) * 128u + (r & 7u) * 16u + (c & 7u) * 2u;
 }
 
-struct Split3 { __nv_bfloat16 b0, b1, b2; };
-__device__ __forceinline__ Split3 split3(float x) {
-    Split3 s;
-    s.b0 = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(s.b0);
-    s.b1 = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(s.b1);
-    s.b2 = __float2bfloat16_rn(r2);
-    return s;
+// x = b0 + b1 + b2 with three bf16 pieces obtained by TRUNCATION (x & 0xffff0000), each capturing 8
+// more significant bits; the residuals are exact in fp32.  4 ALU ops per element + 3 PRMT per pair.
+__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w0, uint32_t& w1, uint32_t& w2) {
+    const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+    w0 = __byte_perm(u0, u1, 0x7632);                       // high halves of (x0, x1)
+    const float r0 = x0 - __uint_as_float(u0 & 0xffff0000u), r1 = x1 - __uint_as_float(u1 & 0xffff0000u);
+    const uint32_t v0 = __float_as_uint(r0), v1 = __float_as_uint(r1);
+    w1 = __byte_perm(v0, v1, 0x7632);
+    const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
+    w2 = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
 }
 __device__ __forceinline__ void store_elem(uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c, float x) {
-    const Split3 s = split3(x);
+    uint32_t w0, w1, w2;
+    split3_pair(x, 0.0f, w0, w1, w2);
     uint8_t* p = sm0 + (m.base + moff(r, c, m.RS));
-    *reinterpret_cast<__nv_bfloat16*>(p) = s.b0;
-    *reinterpret_cast<__nv_bfloat16*>(p + m.part) = s.b1;
-    *reinterpret_cast<__nv_bfloat16*>(p + 2 * m.part) = s.b2;
+    *reinterpret_cast<uint16_t*>(p) = (uint16_t)w0;
+    *reinterpret_cast<uint16_t*>(p + m.part) = (uint16_t)w1;
+    *reinterpret_cast<uint16_t*>(p + 2 * m.part) = (uint16_t)w2;
 }
 // 8 consecutive columns (one 16-byte chunk) of row r
 __device__ __forceinline__ void store_chunk8(uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c0, const float* v) {
     uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const Split3 a = split3(v[2 * j]), b = split3(v[2 * j + 1]);
-        w0[j] = (uint32_t)__bfloat16_as_ushort(a.b0) | ((uint32_t)__bfloat16_as_ushort(b.b0) << 16);
-        w1[j] = (uint32_t)__bfloat16_as_ushort(a.b1) | ((uint32_t)__bfloat16_as_ushort(b.b1) << 16);
-        w2[j] = (uint32_t)__bfloat16_as_ushort(a.b2) | ((uint32_t)__bfloat16_as_ushort(b.b2) << 16);
-    }
+    for (int j = 0; j < 4; ++j) split3_pair(v[2 * j], v[2 * j + 1], w0[j], w1[j], w2[j]);
     uint8_t* p = sm0 + (m.base + moff(r, c0, m.RS));
     *reinterpret_cast<uint4*>(p) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
     *reinterpret_cast<uint4*>(p + m.part) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
     *reinterpret_cast<uint4*>(p + 2 * m.part) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
 }
-__device__ __forceinline__ void load_chunk8(const uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c0, float* v) {
-    const uint8_t* p = sm0 + (m.base + moff(r, c0, m.RS));
-    const uint4 a = *reinterpret_cast<const uint4*>(p);
-    const uint4 b = *reinterpret_cast<const uint4*>(p + m.part);
-    const uint4 c = *reinterpret_cast<const uint4*>(p + 2 * m.part);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, cw[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {   // bf16 -> f32 is a 16-bit shift
-        v[2 * j] = __uint_as_float(aw[j] << 16) + __uint_as_float(bw[j] << 16) + __uint_as_float(cw[j] << 16);
-        v[2 * j + 1] = __uint_as_float(aw[j] & 0xffff0000u) + __uint_as_float(bw[j] & 0xffff0000u) +
-                       __uint_as_float(cw[j] & 0xffff0000u);
-    }
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1) from two MUFU ops; absolute error ~1e-7 (the hidden activations
+// feed 64-term dot products, so absolute -- not relative -- accuracy near 0 is what matters)
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 
-// D[M x N] (+)= A * B^T-like product; operand usage (K-major / MN-major) per flag; issued by 1 thread
-__device__ __forceinline__ void gemm(uint32_t d_tmem, int M, int N, const Mat& A, int a_mn, const Mat& B, int b_mn,
-                                     int K) {
+// D[M x N] = A * B (operand usage K-major / MN-major per flag).  WARP-LEVEL: call from all lanes of
+// one warp; K = 16 * KSTEPS.
+template <int KSTEPS>
+__device__ __forceinline__ void gemm(uint32_t d_tmem, int M, int N, const Mat& A, int a_mn, const Mat& B, int b_mn) {
     const uint32_t a_lbo = a_mn ? A.RS : 128u, a_sbo = a_mn ? 128u : A.RS, a_step = a_mn ? 2u * A.RS : 256u;
     const uint32_t b_lbo = b_mn ? B.RS : 128u, b_sbo = b_mn ? 128u : B.RS, b_step = b_mn ? 2u * B.RS : 256u;
-    umma::gemm_bf16x3(d_tmem, A.base, A.part, a_lbo, a_sbo, a_step, B.base, B.part, b_lbo, b_sbo, b_step,
-                      umma::idesc_bf16(M, N, a_mn, b_mn), K / 16, false);
+    umma::gemm_bf16x3_warp<KSTEPS>(d_tmem, A.base, A.part, a_lbo, a_sbo, a_step, B.base, B.part, b_lbo, b_sbo, b_step,
+                                   umma::idesc_bf16(M, N, a_mn, b_mn));
 }
-// B = block of ones (single exact piece): D[M x 8] = A^T 1, A used MN-major
+// runtime K in {16, 32} (padded observation width)
+__device__ __forceinline__ void gemm_kx(uint32_t d_tmem, int M, int N, const Mat& A, int a_mn, const Mat& B, int b_mn, int K) {
+    if (K == 16) gemm<1>(d_tmem, M, N, A, a_mn, B, b_mn); else gemm<2>(d_tmem, M, N, A, a_mn, B, b_mn);
+}
+// B = block of ones (one exact bf16 piece): D[64 x 8] = A^T 1 over the 128 rows, A used MN-major
 __device__ __forceinline__ void gemm_colsum(uint32_t d_tmem, const Mat& A, uint32_t ones_base, uint32_t ones_RS) {
-    const uint32_t idesc = umma::idesc_bf16(64, 8, 1, 1);
-    uint32_t acc = 0;
-    for (int k = 0; k < kRows / 16; ++k) {
-        const uint64_t bd = umma::smem_desc(ones_base + k * 2u * ones_RS, ones_RS, 128u);
-#pragma unroll
-        for (int p = 2; p >= 0; --p) {
-            const uint64_t ad = umma::smem_desc(A.base + p * A.part + k * 2u * A.RS, A.RS, 128u);
-            umma::mma_bf16(d_tmem, ad, bd, idesc, acc);
-            acc = 1u;
-        }
-    }
+    umma::gemm_bf16x3_warp<kRows / 16, 3, 1>(d_tmem, A.base, A.part, A.RS, 128u, 2u * A.RS, ones_base, 0u, ones_RS, 128u,
+                                             2u * ones_RS, umma::idesc_bf16(64, 8, 1, 1));
 }
 
 struct Smem {   // byte offsets from the dynamic shared memory base (all multiples of 128)
@@ -157,22 +147,38 @@ __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
 
 struct NetG { int64_t w1, b1, w2, b2, w3, b3, ls; };
 
+// Global -> shared staging with U loads in flight per thread (the loads are independent of the
+// stores, so batching them hides the L2 / HBM latency that a load-store-load-store loop exposes).
+template <int U, class LoadF, class StoreF>
+__device__ __forceinline__ void staged_loop(int n, LoadF&& ld, StoreF&& st) {
+    for (int base = 0; base < n; base += kThreads * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = base + u * kThreads + (int)threadIdx.x;
+            v[u] = e < n ? ld(e) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = base + u * kThreads + (int)threadIdx.x;
+            if (e < n) st(e, v[u]);
+        }
+    }
+}
+
 // stage one network's weights: bf16x3 blocked copies for the tensor core + fp32 side copies
 __device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const float* __restrict__ params, const NetG& g,
                               int obs_dim, int out_dim) {
     const int tid = threadIdx.x;
-    for (int e = tid; e < H * S.KXP; e += kThreads) {
-        const int o = e / S.KXP, k = e - o * S.KXP;
-        store_elem(sm0, S.W1, o, k, k < obs_dim ? __ldg(params + g.w1 + (int64_t)o * obs_dim + k) : 0.0f);
-    }
-    for (int e = tid; e < H * H; e += kThreads) store_elem(sm0, S.W2, e >> 6, e & 63, __ldg(params + g.w2 + e));
+    const int KXP = S.KXP;
+    staged_loop<8>(H * KXP,
+                   [&](int e) { const int o = e / KXP, k = e - o * KXP; return k < obs_dim ? __ldg(params + g.w1 + (int64_t)o * obs_dim + k) : 0.0f; },
+                   [&](int e, float x) { const int o = e / KXP, k = e - o * KXP; store_elem(sm0, S.W1, o, k, x); });
+    staged_loop<16>(H * H, [&](int e) { return __ldg(params + g.w2 + e); },
+                    [&](int e, float x) { store_elem(sm0, S.W2, e >> 6, e & 63, x); });
     float* w3f = reinterpret_cast<float*>(sm + S.w3f);
-    for (int e = tid; e < NO * H; e += kThreads) {
-        const int a = e >> 6, k = e & 63;
-        const float w = a < out_dim ? __ldg(params + g.w3 + a * H + k) : 0.0f;
-        store_elem(sm0, S.W3, a, k, w);
-        if (a < kMaxAct) w3f[e] = w;
-    }
+    staged_loop<4>(NO * H, [&](int e) { return (e >> 6) < out_dim ? __ldg(params + g.w3 + e) : 0.0f; },
+                   [&](int e, float x) { store_elem(sm0, S.W3, e >> 6, e & 63, x); if ((e >> 6) < kMaxAct) w3f[e] = x; });
     float* b1 = reinterpret_cast<float*>(sm + S.b1);
     float* b2 = reinterpret_cast<float*>(sm + S.b2);
     float* b3 = reinterpret_cast<float*>(sm + S.b3);
@@ -187,16 +193,19 @@ __device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const fl
 struct Pipe {   // MMA issue / completion handshake
     uint64_t* bar;
     uint32_t phase;
-    // all threads: make smem writes + tcgen05.ld's visible, then thread 0 issues `f` and commits
+    // all threads: make smem writes + tcgen05.ld's visible; then WARP 0 (all lanes, warp-uniform
+    // control flow) runs `f`, whose MMAs are issued by one elected lane, and commits.
     template <class F>
     __device__ __forceinline__ void run(F&& f) {
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
-        if (threadIdx.x == 0) {
+        const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+        if (warp_u == 0) {
             umma::fence_after_sync();
             f();
-            umma::mma_commit(bar);
+            if (umma::elect_one()) umma::mma_commit(bar);
+            __syncwarp();
         }
         umma::mbar_wait(bar, phase);
         phase ^= 1u;
@@ -204,60 +213,54 @@ struct Pipe {   // MMA issue / completion handshake
     }
 };
 
-// TMEM (row = 32*(warp&3)+lane, 32 columns starting at col) -> tanh(x + bias) -> bf16x3 rows of OUT
-__device__ __forceinline__ void epi_tanh(uint8_t* sm, uint8_t* sm0, const Mat& OUT, uint32_t tmem, uint32_t col,
-                                         const float* __restrict__ bias) {
+// Epilogue thread map: warp w -> TMEM sub-partition q = w & 3 (rows 32q + lane), column group
+// cq = w >> 2 -> columns [16 cq, 16 cq + 16) of a 64-wide accumulator.
+// TMEM -> h = tanh(x + bias) -> bf16x3 rows of OUT; h stays in registers for the backward pass
+__device__ __forceinline__ void epi_tanh(uint8_t* sm0, const Mat& OUT, uint32_t tmem, uint32_t col,
+                                         const float* __restrict__ bias, float (&h)[kCols]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
-    float v[32];
-    umma::tmem_ld32(tmem + ((32u * (warp & 3)) << 16) + col + c0, v);
+    const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
+    umma::tmem_ld16(tmem + ((32u * (warp & 3)) << 16) + col + c0, h);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = ppo::tanh_fast(v[j] + bias[c0 + j]);
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) store_chunk8(sm0, OUT, r, c0 + j, v + j);
+    for (int j = 0; j < kCols; ++j) h[j] = tanh_mufu(h[j] + bias[c0 + j]);
+    store_chunk8(sm0, OUT, r, c0, h);
+    store_chunk8(sm0, OUT, r, c0 + 8, h + 8);
 }
-// TMEM dH -> dZ = dH * (1 - h^2) with h read from (and dZ written back to) ACT
-__device__ __forceinline__ void epi_dtanh_inplace(uint8_t* sm0, const Mat& ACT, uint32_t tmem, uint32_t col) {
+// TMEM dH -> dZ = dH * (1 - h^2) written over ACT (h from registers)
+__device__ __forceinline__ void epi_dtanh(uint8_t* sm0, const Mat& ACT, uint32_t tmem, uint32_t col,
+                                          const float (&h)[kCols]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
-    float v[32];
-    umma::tmem_ld32(tmem + ((32u * (warp & 3)) << 16) + col + c0, v);
+    const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
+    float v[kCols];
+    umma::tmem_ld16(tmem + ((32u * (warp & 3)) << 16) + col + c0, v);
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        float h[8];
-        load_chunk8(sm0, ACT, r, c0 + j, h);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = v[j + i] * (1.0f - h[i] * h[i]);
-        store_chunk8(sm0, ACT, r, c0 + j, h);
-    }
+    for (int j = 0; j < kCols; ++j) v[j] = v[j] * fmaf(-h[j], h[j], 1.0f);
+    store_chunk8(sm0, ACT, r, c0, v);
+    store_chunk8(sm0, ACT, r, c0 + 8, v + 8);
 }
-// dZ2 = (dOut W3) * (1 - H2^2), in place over H2 (K = out_dim is tiny: SIMT)
-__device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, const Smem& S, int out_dim) {
+// dZ2 = (dOut W3) * (1 - H2^2) written over H2 (K = out_dim is tiny: SIMT)
+__device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, const Smem& S, int out_dim,
+                                                    const float (&h)[kCols]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
+    const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
     const float* dof = reinterpret_cast<const float*>(sm + S.dof) + r * kMaxAct;
     const float* w3f = reinterpret_cast<const float*>(sm + S.w3f);
-    float dv[kMaxAct];
+    float acc[kCols];
 #pragma unroll
-    for (int a = 0; a < kMaxAct; ++a) dv[a] = a < out_dim ? dof[a] : 0.0f;
+    for (int j = 0; j < kCols; ++j) acc[j] = 0.0f;
+    for (int a = 0; a < out_dim; ++a) {
+        const float dv = dof[a];
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        float h[8], acc[8];
-        load_chunk8(sm0, S.H2, r, c0 + j, h);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-        for (int a = 0; a < out_dim; ++a) {
-            const float4 wa = *reinterpret_cast<const float4*>(w3f + a * H + c0 + j);
-            const float4 wb = *reinterpret_cast<const float4*>(w3f + a * H + c0 + j + 4);
-            acc[0] = fmaf(dv[a], wa.x, acc[0]); acc[1] = fmaf(dv[a], wa.y, acc[1]);
-            acc[2] = fmaf(dv[a], wa.z, acc[2]); acc[3] = fmaf(dv[a], wa.w, acc[3]);
-            acc[4] = fmaf(dv[a], wb.x, acc[4]); acc[5] = fmaf(dv[a], wb.y, acc[5]);
-            acc[6] = fmaf(dv[a], wb.z, acc[6]); acc[7] = fmaf(dv[a], wb.w, acc[7]);
+        for (int j = 0; j < kCols; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(w3f + a * H + c0 + j);
+            acc[j] = fmaf(dv, w.x, acc[j]); acc[j + 1] = fmaf(dv, w.y, acc[j + 1]);
+            acc[j + 2] = fmaf(dv, w.z, acc[j + 2]); acc[j + 3] = fmaf(dv, w.w, acc[j + 3]);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = acc[i] * (1.0f - h[i] * h[i]);
-        store_chunk8(sm0, S.H2, r, c0 + j, h);
     }
+#pragma unroll
+    for (int j = 0; j < kCols; ++j) acc[j] = acc[j] * fmaf(-h[j], h[j], 1.0f);
+    store_chunk8(sm0, S.H2, r, c0, acc);
+    store_chunk8(sm0, S.H2, r, c0 + 8, acc + 8);
 }
 // write one row of dOut: fp32 side copy + bf16x3 operand (columns >= out_dim are zero)
 __device__ __forceinline__ void write_dout_row(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t r, const float* dv) {
@@ -268,13 +271,13 @@ __device__ __forceinline__ void write_dout_row(uint8_t* sm, uint8_t* sm0, const 
     store_chunk8(sm0, S.DO, r, 8, dv + 8);
 }
 
-// weight-gradient accumulators (M = 64: row o = 16*q + lane for lane < 16) -> RED into the flat gradient
+// weight-gradient accumulators (M = 64: row o = 16*q + lane for lane < 16) -> the CTA's partial row
 __device__ __forceinline__ void red_rows(uint32_t tmem, uint32_t col, int ncols, float* __restrict__ grad, int64_t base,
                                          int64_t row_stride, int valid_cols) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, half = warp >> 2;
-    // the two warps of a sub-partition split the column range in 8-column slabs
-    for (int c0 = 8 * half; c0 < ncols; c0 += 16) {
+    const int q = warp & 3, cq = warp >> 2;
+    // the four warps of a sub-partition take 8-column slabs round-robin
+    for (int c0 = 8 * cq; c0 < ncols; c0 += 32) {
         float v[8];
         umma::tmem_ld8(tmem + ((32u * q) << 16) + col + c0, v);
         if (lane < 16) {
@@ -288,41 +291,45 @@ __device__ __forceinline__ void red_rows(uint32_t tmem, uint32_t col, int ncols,
 // transposed variant for dW3^T [k][a] -> grad W3[a][k]
 __device__ __forceinline__ void red_w3(uint32_t tmem, uint32_t col, float* __restrict__ grad, int64_t base, int out_dim) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, cq = warp >> 2;
+    if (cq >= NO / 8) return;      // warp-uniform
     float v[8];
-    umma::tmem_ld8(tmem + ((32u * q) << 16) + col + 8 * half, v);
+    umma::tmem_ld8(tmem + ((32u * q) << 16) + col + 8 * cq, v);
     if (lane < 16) {
         const int k = 16 * q + lane;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int a = 8 * half + j;
+            const int a = 8 * cq + j;
             if (a < out_dim) atomicAdd(grad + base + (int64_t)a * H + k, v[j]);
         }
     }
 }
 
-// forward of one trunk: X -> H1 -> H2 -> head accumulator D3 (TMEM)
-__device__ __forceinline__ void trunk_forward(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, Pipe& pipe) {
-    pipe.run([&] { gemm(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
-    epi_tanh(sm, sm0, S.H1, tmem, cD1, reinterpret_cast<const float*>(sm + S.b1));
-    pipe.run([&] { gemm(tmem + cD2, 128, H, S.H1, 0, S.W2, 0, H); });
-    epi_tanh(sm, sm0, S.H2, tmem, cD2, reinterpret_cast<const float*>(sm + S.b2));
-    pipe.run([&] { gemm(tmem + cD3, 128, NO, S.H2, 0, S.W3, 0, H); });
+// forward of one trunk: X -> H1 -> H2 -> head accumulator D3 (TMEM); h1 / h2 of the thread's
+// (row, 16 columns) stay in registers
+__device__ __forceinline__ void trunk_forward(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, Pipe& pipe,
+                                              float (&h1)[kCols], float (&h2)[kCols]) {
+    pipe.run([&] { gemm_kx(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
+    epi_tanh(sm0, S.H1, tmem, cD1, reinterpret_cast<const float*>(sm + S.b1), h1);
+    pipe.run([&] { gemm<H / 16>(tmem + cD2, 128, H, S.H1, 0, S.W2, 0); });
+    epi_tanh(sm0, S.H2, tmem, cD2, reinterpret_cast<const float*>(sm + S.b2), h2);
+    pipe.run([&] { gemm<H / 16>(tmem + cD3, 128, NO, S.H2, 0, S.W3, 0); });
 }
 
-// backward of one trunk given dOut (S.DO / dof); REDs all weight and bias gradients of the net
+// backward of one trunk given dOut (S.DO / dof); writes all weight and bias gradients of the net
 __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, Pipe& pipe,
-                                               const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad) {
-    pipe.run([&] { gemm(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1, kRows); });          // dW3^T = H2^T dOut
-    epi_head_input_grad(sm, sm0, S, out_dim);                                         // H2 := dZ2
+                                               const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad,
+                                               const float (&h1)[kCols], const float (&h2)[kCols]) {
+    pipe.run([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });      // dW3^T = H2^T dOut
+    epi_head_input_grad(sm, sm0, S, out_dim, h2);                                     // H2 := dZ2
     pipe.run([&] {
-        gemm(tmem + cDW2, 64, H, S.H2, 1, S.H1, 1, kRows);                            // dW2 = dZ2^T H1
+        gemm<kRows / 16>(tmem + cDW2, 64, H, S.H2, 1, S.H1, 1);                       // dW2 = dZ2^T H1
         gemm_colsum(tmem + cDB2, S.H2, S.ONES, S.ONES_RS);                            // db2 = dZ2^T 1
-        gemm(tmem + cDH1, 128, H, S.H2, 0, S.W2, 1, H);                               // dH1 = dZ2 W2
+        gemm<H / 16>(tmem + cDH1, 128, H, S.H2, 0, S.W2, 1);                          // dH1 = dZ2 W2
     });
-    epi_dtanh_inplace(sm0, S.H1, tmem, cDH1);                                         // H1 := dZ1
+    epi_dtanh(sm0, S.H1, tmem, cDH1, h1);                                             // H1 := dZ1
     pipe.run([&] {
-        gemm(tmem + cDW1, 64, S.KXP, S.H1, 1, S.X, 1, kRows);                         // dW1 = dZ1^T X
+        gemm<kRows / 16>(tmem + cDW1, 64, S.KXP, S.H1, 1, S.X, 1);                    // dW1 = dZ1^T X
         gemm_colsum(tmem + cDB1, S.H1, S.ONES, S.ONES_RS);                            // db1 = dZ1^T 1
     });
     red_w3(tmem, cDW3, grad, g.w3, out_dim);
@@ -338,12 +345,43 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// State of the in-kernel grid barriers of the fused step (self-resetting; launches are stream-ordered
+// and every CTA of the grid is resident: grid <= #SMs, 1 CTA / SM).
+__device__ unsigned int g_step_bar[2] = {0u, 0u};
+__device__ unsigned int g_step_depart = 0u;
+__device__ double g_step_ss = 0.0;
+
+struct AdamArgs {     // optimiser half of the fused single-GPU step
+    float* params_w;
+    float* grad_scratch;   // n_params + TS_PPO_GRAD_EXTRA folded values (loss sums are read back from here)
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t* step_count;
+    float* stats_row;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (*((volatile unsigned int*)ctr) < gridDim.x) {}
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// FUSE_ADAM = false: write this CTA's partial gradient row and stop (multi-GPU: fold + all-reduce +
+// ts_clip_adam_step follow).  FUSE_ADAM = true: after a grid barrier every CTA folds its slice of the
+// gradient over all partial rows, a second barrier publishes the global sum of squares, then the slice's
+// clip + Adam update is applied in place -- the whole optimiser step is ONE launch.
+template <bool FUSE_ADAM>
 __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
     const float* __restrict__ params, const ts_actor_critic_desc d, const ts_ppo_hparams hp,
     const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ adv,
     const float* __restrict__ ret, const float* __restrict__ logp_old, const float* __restrict__ v_s,
     const int32_t* __restrict__ perm, int64_t lo, int64_t hi, int64_t global_rows,
-    const float* __restrict__ adv_moments, float* __restrict__ partials) {
+    const float* __restrict__ adv_moments, float* __restrict__ partials, const AdamArgs opt) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_bar;
@@ -379,23 +417,24 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
         const int64_t pos0 = lo + t * kRows;
         const int nrows = (int)tsb::imin((int64_t)kRows, hi - pos0);
         // ---- tile inputs -----------------------------------------------------------------------
-        for (int e = tid; e < kRows * S.KXP; e += kThreads) {
-            const int r = e / S.KXP, k = e - r * S.KXP;
-            float x = 0.0f;
-            if (r < nrows && k < d.obs_dim) {
-                const int64_t row = perm ? (int64_t)perm[pos0 + r] : pos0 + r;
-                x = __ldg(obs + row * d.obs_dim + k);
-            }
-            store_elem(sm0, S.X, r, k, x);
-        }
-        for (int e = tid; e < kRows * kMaxAct; e += kThreads) {
-            const int r = e / kMaxAct, a = e - r * kMaxAct;
-            float x = 0.0f;
-            if (r < nrows && a < A) {
-                const int64_t row = perm ? (int64_t)perm[pos0 + r] : pos0 + r;
-                x = __ldg(act + row * A + a);
-            }
-            actt[e] = x;
+        {
+            const int KXP = S.KXP, OBS = d.obs_dim;
+            staged_loop<16>(kRows * KXP,
+                            [&](int e) {
+                                const int r = e / KXP, k = e - r * KXP;
+                                if (r >= nrows || k >= OBS) return 0.0f;
+                                const int64_t row = perm ? (int64_t)__ldg(perm + pos0 + r) : pos0 + r;
+                                return __ldg(obs + row * OBS + k);
+                            },
+                            [&](int e, float x) { const int r = e / KXP, k = e - r * KXP; store_elem(sm0, S.X, r, k, x); });
+            staged_loop<8>(kRows * kMaxAct,
+                           [&](int e) {
+                               const int r = e / kMaxAct, a = e - r * kMaxAct;
+                               if (r >= nrows || a >= A) return 0.0f;
+                               const int64_t row = perm ? (int64_t)__ldg(perm + pos0 + r) : pos0 + r;
+                               return __ldg(act + row * A + a);
+                           },
+                           [&](int e, float x) { actt[e] = x; });
         }
         if (tid < kRows) {
             float a_ = 0.f, r_ = 0.f, l_ = 0.f, v_ = 0.f;
@@ -408,8 +447,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
         if (tid < 64) red[tid] = 0.0f;
 
         // ================= critic ================================================================
+        float h1[kCols], h2[kCols];
         stage_weights(sm, sm0, S, params, gc, d.obs_dim, 1);
-        trunk_forward(sm, sm0, S, tmem, pipe);
+        trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
         float vf_row = 0.0f;
         if (tid < kRows) {
             float v16[16], dv[kMaxAct];
@@ -424,13 +464,13 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
             const float sdv = warp_sum(dv[0]);
             if (lane == 0) atomicAdd(red + 0, sdv);            // db3 (critic)
         }
-        trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad);
+        trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2);
         __syncthreads();
         if (tid == 0) { atomicAdd(grad + gc.b3, red[0]); red[0] = 0.0f; }
 
         // ================= actor =================================================================
         stage_weights(sm, sm0, S, params, ga, d.obs_dim, A);
-        trunk_forward(sm, sm0, S, tmem, pipe);
+        trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
         float clip_row = 0.0f;
         if (tid < kRows) {
             const int r = tid;
@@ -469,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
                 }
             }
         }
-        trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad);
+        trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2);
 
         // ================= loss sums + small gradients ===========================================
         const float s_clip = warp_sum(tid < kRows ? clip_row : 0.0f);
@@ -521,7 +561,7 @@ __host__ __device__ inline SmemF make_smem_f(int obs_dim, uint32_t sbase) {
     s.b2 = o;   o += H * 4;
     s.b3 = o;   o += kMaxAct * 4;
     s.ls = o;   o += kMaxAct * 4;
-    s.part = o; o += 2 * kRows * kMaxAct * 4;   // head partial sums of the two column halves
+    s.part = o; o += 4 * kRows * kMaxAct * 4;   // head partial sums of the four column groups
     s.total = o;
     return s;
 }
@@ -545,11 +585,14 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
     if (warp == 0) umma::tmem_alloc(&s_tmem, 128);
     if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
     // weights: W1, W2 as tensor-core operands; head weights / biases as fp32
-    for (int e = tid; e < H * S.KXP; e += kThreads) {
-        const int o = e / S.KXP, k = e - o * S.KXP;
-        store_elem(sm0, S.W1, o, k, k < d.obs_dim ? __ldg(params + g.w1 + (int64_t)o * d.obs_dim + k) : 0.0f);
+    {
+        const int KXP = S.KXP, OBS = d.obs_dim;
+        staged_loop<8>(H * KXP,
+                       [&](int e) { const int o = e / KXP, k = e - o * KXP; return k < OBS ? __ldg(params + g.w1 + (int64_t)o * OBS + k) : 0.0f; },
+                       [&](int e, float x) { const int o = e / KXP, k = e - o * KXP; store_elem(sm0, S.W1, o, k, x); });
+        staged_loop<16>(H * H, [&](int e) { return __ldg(params + g.w2 + e); },
+                        [&](int e, float x) { store_elem(sm0, S.W2, e >> 6, e & 63, x); });
     }
-    for (int e = tid; e < H * H; e += kThreads) store_elem(sm0, S.W2, e >> 6, e & 63, __ldg(params + g.w2 + e));
     float* w3f = reinterpret_cast<float*>(sm + S.w3f);
     float* b1 = reinterpret_cast<float*>(sm + S.b1);
     float* b2 = reinterpret_cast<float*>(sm + S.b2);
@@ -576,23 +619,31 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
         const int nrows = (int)tsb::imin((int64_t)kRows, n - row0);
         const float* src = (MODE == 0 && second) ? in1 : in0;
         // the tile's rows are contiguous in memory: coalesced read, scattered bf16x3 store
-        for (int e = tid; e < kRows * S.KXP; e += kThreads) {
-            const int r = e / S.KXP, k = e - r * S.KXP;
-            store_elem(sm0, S.X, r, k, (r < nrows && k < d.obs_dim) ? __ldg(src + (row0 + r) * d.obs_dim + k) : 0.0f);
+        {
+            const int KXP = S.KXP, OBS = d.obs_dim;
+            staged_loop<16>(kRows * KXP,
+                            [&](int e) {
+                                const int r = e / KXP, k = e - r * KXP;
+                                return (r < nrows && k < OBS) ? __ldg(src + (row0 + r) * OBS + k) : 0.0f;
+                            },
+                            [&](int e, float x) { const int r = e / KXP, k = e - r * KXP; store_elem(sm0, S.X, r, k, x); });
         }
-        pipe.run([&] { gemm(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
-        epi_tanh(sm, sm0, S.H1, tmem, cD1, b1);
-        pipe.run([&] { gemm(tmem + cD2, 128, H, S.H1, 0, S.W2, 0, H); });
-        {   // h2 = tanh(D2 + b2) stays in registers; head = h2 . W3^T (K = 64 split over the two column halves)
-            const uint32_t r = 32u * (warp & 3) + lane, c0 = 32u * (warp >> 2);
-            float v[32];
-            umma::tmem_ld32(tmem + ((32u * (warp & 3)) << 16) + cD2 + c0, v);
+        pipe.run([&] { gemm_kx(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
+        {
+            float h1[kCols];
+            epi_tanh(sm0, S.H1, tmem, cD1, b1, h1);
+        }
+        pipe.run([&] { gemm<H / 16>(tmem + cD2, 128, H, S.H1, 0, S.W2, 0); });
+        {   // h2 = tanh(D2 + b2) stays in registers; head = h2 . W3^T (K = 64 split over the four column groups)
+            const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
+            float v[kCols];
+            umma::tmem_ld16(tmem + ((32u * (warp & 3)) << 16) + cD2 + c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ppo::tanh_fast(v[j] + b2[c0 + j]);
+            for (int j = 0; j < kCols; ++j) v[j] = tanh_mufu(v[j] + b2[c0 + j]);
             for (int a = 0; a < out_dim; ++a) {
                 float acc = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc = fmaf(v[j], w3f[a * H + c0 + j], acc);
+                for (int j = 0; j < kCols; ++j) acc = fmaf(v[j], w3f[a * H + c0 + j], acc);
                 part[((warp >> 2) * kRows + r) * kMaxAct + a] = acc;
             }
         }
@@ -600,11 +651,13 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
         if (tid < nrows) {
             const int r = tid;
             if (MODE == 0) {
-                (second ? out1 : out0)[row0 + r] = part[r * kMaxAct] + part[(kRows + r) * kMaxAct] + b3[0];
+                (second ? out1 : out0)[row0 + r] = (part[r * kMaxAct] + part[(kRows + r) * kMaxAct]) +
+                                                   (part[(2 * kRows + r) * kMaxAct] + part[(3 * kRows + r) * kMaxAct]) + b3[0];
             } else {
                 float lp = 0.0f;
                 for (int a = 0; a < out_dim; ++a) {
-                    const float mu = part[r * kMaxAct + a] + part[(kRows + r) * kMaxAct + a] + b3[a];
+                    const float mu = (part[r * kMaxAct + a] + part[(kRows + r) * kMaxAct + a]) +
+                                     (part[(2 * kRows + r) * kMaxAct + a] + part[(3 * kRows + r) * kMaxAct + a]) + b3[a];
                     lp += ppo::normal_logp_term(__ldg(in1 + (row0 + r) * out_dim + a), mu, expf(ls[a]));
                     if (out1) out1[(row0 + r) * out_dim + a] = mu;
                 }
@@ -631,14 +684,35 @@ int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const
     const size_t smem = make_smem(d.obs_dim, 0).total;
     static size_t configured = 0;
     if (smem > configured) {
-        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int64_t tiles = (hi - lo + kRows - 1) / kRows;
     const unsigned grid = (unsigned)imin(tiles, num_sms());
-    ppo_grad_tc_kernel<<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi,
-                                                     global_rows, adv_moments, grad);
+    ppo_grad_tc_kernel<false><<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi,
+                                                            global_rows, adv_moments, grad, AdamArgs{});
     return check_launch("ts_ppo_grad(tc)");
+}
+
+// one whole optimiser step (minibatch fwd/bwd + gradient fold + clip + Adam + stats) in ONE launch
+int launch_ppo_step_tc(float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
+                       const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
+                       const int32_t* perm, int64_t lo, int64_t hi, const float* adv_moments, float* partials,
+                       float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count, float* stats_row,
+                       cudaStream_t st) {
+    const size_t smem = make_smem(d.obs_dim, 0).total;
+    static size_t configured = 0;
+    if (smem > configured) {
+        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int64_t tiles = (hi - lo + kRows - 1) / kRows;
+    const unsigned grid = (unsigned)imin(tiles, num_sms());   // all CTAs co-resident (1 per SM): grid barriers are safe
+    const AdamArgs opt{params, grad_scratch, exp_avg, exp_avg_sq, step_count, stats_row};
+    ppo_grad_tc_kernel<true><<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi,
+                                                           hi - lo, adv_moments, partials, opt);
+    return check_launch("ts_ppo_step(tc)");
 }
 
 int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,

@@ -162,6 +162,60 @@ __device__ __forceinline__ void gemm_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint
     }
 }
 
+// One lane of a converged warp (elect.sync).  MMA issue code must be WARP-UNIFORM: run it in a
+// whole warp and predicate the tcgen05 instructions with this, so that descriptors stay in uniform
+// registers (a divergent `if (threadIdx.x == 0)` makes ptxas wrap every UTCHMMA in an election loop).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// Descriptor halves: lo32 = (addr>>4) | (LBO>>4)<<16 ; hi32 = (SBO>>4) | version(1)<<14.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+// Warp-level version of gemm_bf16x3 with a compile-time K-step count: call from ALL lanes of one
+// warp; one elected lane issues the 6*KSTEPS MMAs.  `pieces` = 3 (full) or 1 (operand is exact in bf16).
+template <int KSTEPS, int A_PIECES = 3, int B_PIECES = 3>
+__device__ __forceinline__ void gemm_bf16x3_warp(uint32_t d_tmem, uint32_t a0, uint32_t a_part, uint32_t a_lbo, uint32_t a_sbo,
+                                                 uint32_t a_step, uint32_t b0, uint32_t b_part, uint32_t b_lbo, uint32_t b_sbo,
+                                                 uint32_t b_step, uint32_t idesc) {
+    const uint32_t ahi = desc_hi(a_sbo), bhi = desc_hi(b_sbo);
+    uint32_t alo[3], blo[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        alo[p] = desc_lo(a0 + (p < A_PIECES ? p : 0) * a_part, a_lbo);
+        blo[p] = desc_lo(b0 + (p < B_PIECES ? p : 0) * b_part, b_lbo);
+    }
+    const uint32_t astep = a_step >> 4, bstep = b_step >> 4;
+    if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+            uint64_t A[3], B[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                A[p] = desc_pack(alo[p] + k * astep, ahi);
+                B[p] = desc_pack(blo[p] + k * bstep, bhi);
+            }
+            bool first = (k == 0);
+            // smallest terms first; pairs (i, j) with i + j <= 2
+            if (A_PIECES == 3) { mma_bf16(d_tmem, A[2], B[0], idesc, first ? 0u : 1u); first = false; }
+            if (B_PIECES == 3) { mma_bf16(d_tmem, A[0], B[2], idesc, first ? 0u : 1u); first = false; }
+            if (A_PIECES == 3 && B_PIECES == 3) { mma_bf16(d_tmem, A[1], B[1], idesc, first ? 0u : 1u); first = false; }
+            if (A_PIECES == 3) { mma_bf16(d_tmem, A[1], B[0], idesc, first ? 0u : 1u); first = false; }
+            if (B_PIECES == 3) { mma_bf16(d_tmem, A[0], B[1], idesc, first ? 0u : 1u); first = false; }
+            mma_bf16(d_tmem, A[0], B[0], idesc, first ? 0u : 1u);
+        }
+    }
+    __syncwarp();
+}
+
 // fp32-faithful product from three bf16 pieces per operand (x = b0 + b1 + b2, 24 bits): keep the
 // six partial products of weight >= 2^-16; part p of an operand lives `part_bytes` after part p-1.
 __device__ __forceinline__ void gemm_bf16x3(uint32_t d_tmem, uint32_t a0, uint32_t a_part, uint32_t a_lbo, uint32_t a_sbo,
