@@ -285,6 +285,10 @@ int ts_narrow_i64_i32(const int64_t* src, int64_t n, int32_t* dst, ts_stream_t s
 int ts_umma_selftest(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K,
                      int32_t dtype, int32_t a_mn, int32_t b_mn, int32_t swap, ts_stream_t stream);
 
+/* Diagnostics: enable / read the phase timeline (32 x %globaltimer ns) that CTA 0 of the tensor-core
+ * PPO step kernel records (csrc/mlp_tc.cu). */
+int ts_tc_timeline(int32_t enable, uint64_t* out32 /* host, nullable */);
+
 #ifdef __cplusplus
 }
 #endif

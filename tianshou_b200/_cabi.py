@@ -84,6 +84,7 @@ SIGNATURES: dict[str, list[Any]] = {
                       C.POINTER(_I64), _I32, _I32, _D, _D, _P, _D, _P, _P, _P, _P],
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
     "ts_narrow_i64_i32": [_P, _I64, _P, _P],
+    "ts_tc_timeline": [_I32, _P],
     "ts_umma_selftest": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 OTHER_SYMBOLS = ["ts_version", "ts_last_error", "ts_launch_count", "ts_reset_launch_count",

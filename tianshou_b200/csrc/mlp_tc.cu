@@ -41,6 +41,19 @@ constexpr int NO = 16;            // padded head width (N of the head GEMM, colu
 constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, cDH1 = 192, cDW2 = 256, cDB2 = 320, cDW3 = 352, cDW1 = 384, cDB1 = 448;
 constexpr uint32_t kTmemCols = 512;
 
+// Optional phase timeline (diagnostics): when g_tc_timeline != nullptr, CTA 0 / thread 0 stores
+// %globaltimer at each phase boundary; read back with ts_tc_timeline().
+__device__ unsigned long long g_tc_timeline[32];
+__device__ int g_tc_timeline_on = 0;
+__device__ __forceinline__ void tstamp(int slot) {
+    if (g_tc_timeline_on && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_tc_timeline[slot] = t;
+    }
+}
+
+
 // ---- bf16x3 operand matrices in shared memory --------------------------------------------------
 struct Mat {
     uint32_t base;   // shared address of piece 0
@@ -147,6 +160,27 @@ __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
 
 struct NetG { int64_t w1, b1, w2, b2, w3, b3, ls; };
 
+// Stage a [rows x cols] fp32 matrix (row pointer by functor, cols padded with zeros up to ncols_pad)
+// into a bf16x3 operand: one thread = one (row, 8-column chunk) -> 8 loads in flight, 3 STS.128, no
+// integer division (chunks per row is a power of two).
+template <class RowPtrF>
+__device__ __forceinline__ void stage_chunks(uint8_t* sm0, const Mat& M, int rows, int cols, int cols_pad,
+                                             RowPtrF&& rowptr) {
+    const int nch = cols_pad >> 3;                 // 2, 4 or 8
+    const int sh = nch == 8 ? 3 : (nch == 4 ? 2 : 1);
+    for (int task = threadIdx.x; task < rows * nch; task += kThreads) {
+        const int r = task >> sh, ch = task & (nch - 1);
+        const float* src = rowptr(r);              // nullptr -> zero row
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = 8 * ch + j;
+            v[j] = (src != nullptr && k < cols) ? __ldg(src + k) : 0.0f;
+        }
+        store_chunk8(sm0, M, r, 8 * ch, v);
+    }
+}
+
 // Global -> shared staging with U loads in flight per thread (the loads are independent of the
 // stores, so batching them hides the L2 / HBM latency that a load-store-load-store loop exposes).
 template <int U, class LoadF, class StoreF>
@@ -170,15 +204,11 @@ __device__ __forceinline__ void staged_loop(int n, LoadF&& ld, StoreF&& st) {
 __device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const float* __restrict__ params, const NetG& g,
                               int obs_dim, int out_dim) {
     const int tid = threadIdx.x;
-    const int KXP = S.KXP;
-    staged_loop<8>(H * KXP,
-                   [&](int e) { const int o = e / KXP, k = e - o * KXP; return k < obs_dim ? __ldg(params + g.w1 + (int64_t)o * obs_dim + k) : 0.0f; },
-                   [&](int e, float x) { const int o = e / KXP, k = e - o * KXP; store_elem(sm0, S.W1, o, k, x); });
-    staged_loop<16>(H * H, [&](int e) { return __ldg(params + g.w2 + e); },
-                    [&](int e, float x) { store_elem(sm0, S.W2, e >> 6, e & 63, x); });
+    stage_chunks(sm0, S.W1, H, obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * obs_dim; });
+    stage_chunks(sm0, S.W2, H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; });
+    stage_chunks(sm0, S.W3, NO, H, H, [&](int a) { return a < out_dim ? params + g.w3 + (int64_t)a * H : (const float*)nullptr; });
     float* w3f = reinterpret_cast<float*>(sm + S.w3f);
-    staged_loop<4>(NO * H, [&](int e) { return (e >> 6) < out_dim ? __ldg(params + g.w3 + e) : 0.0f; },
-                   [&](int e, float x) { store_elem(sm0, S.W3, e >> 6, e & 63, x); if ((e >> 6) < kMaxAct) w3f[e] = x; });
+    for (int e = tid; e < kMaxAct * H; e += kThreads) w3f[e] = (e >> 6) < out_dim ? __ldg(params + g.w3 + e) : 0.0f;
     float* b1 = reinterpret_cast<float*>(sm + S.b1);
     float* b2 = reinterpret_cast<float*>(sm + S.b2);
     float* b3 = reinterpret_cast<float*>(sm + S.b3);
@@ -321,17 +351,22 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
                                                const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad,
                                                const float (&h1)[kCols], const float (&h2)[kCols]) {
     pipe.run([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });      // dW3^T = H2^T dOut
-    epi_head_input_grad(sm, sm0, S, out_dim, h2);                                     // H2 := dZ2
+    tstamp(16);
+    epi_head_input_grad(sm, sm0, S, out_dim, h2);
+    tstamp(17);                                     // H2 := dZ2
     pipe.run([&] {
         gemm<kRows / 16>(tmem + cDW2, 64, H, S.H2, 1, S.H1, 1);                       // dW2 = dZ2^T H1
         gemm_colsum(tmem + cDB2, S.H2, S.ONES, S.ONES_RS);                            // db2 = dZ2^T 1
         gemm<H / 16>(tmem + cDH1, 128, H, S.H2, 0, S.W2, 1);                          // dH1 = dZ2 W2
     });
+    tstamp(18);
     epi_dtanh(sm0, S.H1, tmem, cDH1, h1);                                             // H1 := dZ1
+    tstamp(19);
     pipe.run([&] {
         gemm<kRows / 16>(tmem + cDW1, 64, S.KXP, S.H1, 1, S.X, 1);                    // dW1 = dZ1^T X
         gemm_colsum(tmem + cDB1, S.H1, S.ONES, S.ONES_RS);                            // db1 = dZ1^T 1
     });
+    tstamp(20);
     red_w3(tmem, cDW3, grad, g.w3, out_dim);
     red_rows(tmem, cDW2, H, grad, g.w2, H, H);
     red_rows(tmem, cDB2, 8, grad, g.b2, 1, 1);
@@ -413,28 +448,20 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
     float* actt = reinterpret_cast<float*>(sm + S.act);
 
     const int64_t tiles = (hi - lo + kRows - 1) / kRows;
+    tstamp(0);
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int64_t pos0 = lo + t * kRows;
         const int nrows = (int)tsb::imin((int64_t)kRows, hi - pos0);
         // ---- tile inputs -----------------------------------------------------------------------
-        {
-            const int KXP = S.KXP, OBS = d.obs_dim;
-            staged_loop<16>(kRows * KXP,
-                            [&](int e) {
-                                const int r = e / KXP, k = e - r * KXP;
-                                if (r >= nrows || k >= OBS) return 0.0f;
-                                const int64_t row = perm ? (int64_t)__ldg(perm + pos0 + r) : pos0 + r;
-                                return __ldg(obs + row * OBS + k);
-                            },
-                            [&](int e, float x) { const int r = e / KXP, k = e - r * KXP; store_elem(sm0, S.X, r, k, x); });
-            staged_loop<8>(kRows * kMaxAct,
-                           [&](int e) {
-                               const int r = e / kMaxAct, a = e - r * kMaxAct;
-                               if (r >= nrows || a >= A) return 0.0f;
-                               const int64_t row = perm ? (int64_t)__ldg(perm + pos0 + r) : pos0 + r;
-                               return __ldg(act + row * A + a);
-                           },
-                           [&](int e, float x) { actt[e] = x; });
+        stage_chunks(sm0, S.X, kRows, d.obs_dim, S.KXP, [&](int r) {
+            if (r >= nrows) return (const float*)nullptr;
+            const int64_t row = perm ? (int64_t)__ldg(perm + pos0 + r) : pos0 + r;
+            return obs + row * d.obs_dim;
+        });
+        if (tid < kRows) {   // the row's actions (fp32, read back by the same thread in the loss epilogue)
+            const int64_t row = (tid < nrows) ? (perm ? (int64_t)__ldg(perm + pos0 + tid) : pos0 + tid) : -1;
+#pragma unroll
+            for (int a = 0; a < kMaxAct; ++a) actt[tid * kMaxAct + a] = (row >= 0 && a < A) ? __ldg(act + row * A + a) : 0.0f;
         }
         if (tid < kRows) {
             float a_ = 0.f, r_ = 0.f, l_ = 0.f, v_ = 0.f;
@@ -448,8 +475,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
 
         // ================= critic ================================================================
         float h1[kCols], h2[kCols];
+        tstamp(1);
         stage_weights(sm, sm0, S, params, gc, d.obs_dim, 1);
+        tstamp(2);
         trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
+        tstamp(3);
         float vf_row = 0.0f;
         if (tid < kRows) {
             float v16[16], dv[kMaxAct];
@@ -464,13 +494,17 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
             const float sdv = warp_sum(dv[0]);
             if (lane == 0) atomicAdd(red + 0, sdv);            // db3 (critic)
         }
+        tstamp(4);
         trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2);
+        tstamp(5);
         __syncthreads();
         if (tid == 0) { atomicAdd(grad + gc.b3, red[0]); red[0] = 0.0f; }
 
         // ================= actor =================================================================
         stage_weights(sm, sm0, S, params, ga, d.obs_dim, A);
+        tstamp(6);
         trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
+        tstamp(7);
         float clip_row = 0.0f;
         if (tid < kRows) {
             const int r = tid;
@@ -509,7 +543,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
                 }
             }
         }
+        tstamp(8);
         trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2);
+        tstamp(9);
 
         // ================= loss sums + small gradients ===========================================
         const float s_clip = warp_sum(tid < kRows ? clip_row : 0.0f);
@@ -535,6 +571,102 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+
+    if (FUSE_ADAM) {
+        // ---- gradient fold over the partial rows of all CTAs (fixed order, L2 resident) ------------
+        __shared__ float s_part[4][128];
+        __shared__ double s_red[4];
+        __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
+        const int P = (int)gridDim.x;
+        const int64_t width = d.n_params + TS_PPO_GRAD_EXTRA;
+        const int64_t slice = (width + P - 1) / P;
+        const int64_t i0 = (int64_t)blockIdx.x * slice;
+        const int64_t i1 = tsb::imin(i0 + slice, width);
+        const int e = tid & 127, q = tid >> 7;
+        const int64_t step = *opt.step_count + 1;
+        tstamp(10);
+        grid_barrier(&g_step_bar[0]);                               // every partial row is complete
+        tstamp(11);
+        double ss = 0.0;
+        for (int64_t c = i0; c < i1; c += 128) {
+            const int64_t i = c + e;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (i < i1) {
+                int p = q;
+                for (; p + 28 < P; p += 32) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[u] += __ldcg(partials + (int64_t)(p + 4 * u) * width + i);
+                }
+                for (; p < P; p += 4) acc[0] += __ldcg(partials + (int64_t)p * width + i);
+            }
+            s_part[q][e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            __syncthreads();
+            if (q == 0 && i < i1) {
+                const float g = (s_part[0][e] + s_part[1][e]) + (s_part[2][e] + s_part[3][e]);
+                opt.grad_scratch[i] = g;
+                if (i < d.n_params) ss += (double)g * (double)g;
+            }
+            __syncthreads();
+        }
+        if (tid < 128) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) ss += tsb::shfl_xor_f64(ss, off);
+            if (lane == 0) s_red[warp] = ss;
+        }
+        __syncthreads();
+        tstamp(12);
+        if (tid == 0) atomicAdd(&g_step_ss, (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]));
+        grid_barrier(&g_step_bar[1]);
+        tstamp(13);                               // global sum of squares is complete
+        if (tid == 0) {
+            const float total_norm = (float)sqrt(*((volatile double*)&g_step_ss));
+            float coef = 1.0f;
+            if (hp.max_grad_norm > 0.0) {   // torch.nn.utils.clip_grad_norm_
+                coef = (float)hp.max_grad_norm / (total_norm + 1e-6f);
+                coef = fminf(coef, 1.0f);
+            }
+            s_coef = coef; s_norm = total_norm;
+            const double bc1 = 1.0 - pow(hp.beta1, (double)step);
+            const double bc2 = 1.0 - pow(hp.beta2, (double)step);
+            s_step_size = (float)(hp.lr / bc1);
+            s_bc2_sqrt = (float)sqrt(bc2);
+        }
+        __syncthreads();
+        const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+        const float w1 = (float)(1.0 - hp.beta1), w2 = (float)(1.0 - hp.beta2);
+        const float beta2 = (float)hp.beta2, adam_eps = (float)hp.adam_eps, wd = (float)hp.weight_decay;
+        for (int64_t i = i0 + tid; i < i1 && i < d.n_params; i += kThreads) {
+            float g = opt.grad_scratch[i] * coef;
+            float pv = opt.params_w[i];
+            if (wd != 0.0f) g = fmaf(wd, pv, g);
+            float m = opt.exp_avg[i], v = opt.exp_avg_sq[i];
+            m = m + w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
+            v = v * beta2 + w2 * g * g;                 // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+            const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
+            pv = pv - step_size * (m / denom);          // addcdiv_(exp_avg, denom, -step_size)
+            opt.exp_avg[i] = m; opt.exp_avg_sq[i] = v; opt.params_w[i] = pv;
+        }
+        if (tid == 0) {
+            if (blockIdx.x == 0) {
+                const float* ex = opt.grad_scratch + d.n_params;
+                const float e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
+                const float rows = e3 > 0.0f ? e3 : 1.0f;
+                const float clip_loss = -e0 / rows, vf_loss = e1 / rows, ent_loss = e2 / rows;
+                if (opt.stats_row) {
+                    float* sr = opt.stats_row;
+                    sr[0] = clip_loss + (float)hp.vf_coef * vf_loss - (float)hp.ent_coef * ent_loss;
+                    sr[1] = clip_loss; sr[2] = vf_loss; sr[3] = ent_loss;
+                    sr[4] = s_norm; sr[5] = e3; sr[6] = 0.0f; sr[7] = 0.0f;
+                }
+                *opt.step_count = step;
+            }
+            tstamp(14);
+            if (atomicAdd(&g_step_depart, 1u) == gridDim.x - 1) {
+                g_step_bar[0] = 0u; g_step_bar[1] = 0u; g_step_depart = 0u; g_step_ss = 0.0;
+                __threadfence();
+            }
+        }
+    }
 }
 
 
@@ -585,14 +717,8 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
     if (warp == 0) umma::tmem_alloc(&s_tmem, 128);
     if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
     // weights: W1, W2 as tensor-core operands; head weights / biases as fp32
-    {
-        const int KXP = S.KXP, OBS = d.obs_dim;
-        staged_loop<8>(H * KXP,
-                       [&](int e) { const int o = e / KXP, k = e - o * KXP; return k < OBS ? __ldg(params + g.w1 + (int64_t)o * OBS + k) : 0.0f; },
-                       [&](int e, float x) { const int o = e / KXP, k = e - o * KXP; store_elem(sm0, S.W1, o, k, x); });
-        staged_loop<16>(H * H, [&](int e) { return __ldg(params + g.w2 + e); },
-                        [&](int e, float x) { store_elem(sm0, S.W2, e >> 6, e & 63, x); });
-    }
+    stage_chunks(sm0, S.W1, H, d.obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * d.obs_dim; });
+    stage_chunks(sm0, S.W2, H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; });
     float* w3f = reinterpret_cast<float*>(sm + S.w3f);
     float* b1 = reinterpret_cast<float*>(sm + S.b1);
     float* b2 = reinterpret_cast<float*>(sm + S.b2);
@@ -619,15 +745,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
         const int nrows = (int)tsb::imin((int64_t)kRows, n - row0);
         const float* src = (MODE == 0 && second) ? in1 : in0;
         // the tile's rows are contiguous in memory: coalesced read, scattered bf16x3 store
-        {
-            const int KXP = S.KXP, OBS = d.obs_dim;
-            staged_loop<16>(kRows * KXP,
-                            [&](int e) {
-                                const int r = e / KXP, k = e - r * KXP;
-                                return (r < nrows && k < OBS) ? __ldg(src + (row0 + r) * OBS + k) : 0.0f;
-                            },
-                            [&](int e, float x) { const int r = e / KXP, k = e - r * KXP; store_elem(sm0, S.X, r, k, x); });
-        }
+        stage_chunks(sm0, S.X, kRows, d.obs_dim, S.KXP, [&](int r) {
+            return r < nrows ? src + (row0 + r) * d.obs_dim : (const float*)nullptr;
+        });
         pipe.run([&] { gemm_kx(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
         {
             float h1[kCols];
@@ -671,6 +791,13 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
 }
 
 }  // namespace
+
+extern "C" int ts_tc_timeline(int32_t enable, uint64_t* out32 /* host, nullable */) {
+    int on = enable;
+    TS_CUDA(cudaMemcpyToSymbol(g_tc_timeline_on, &on, sizeof(int)));
+    if (out32) TS_CUDA(cudaMemcpyFromSymbol(out32, g_tc_timeline, 32 * sizeof(unsigned long long)));
+    return 0;
+}
 
 namespace tsb {
 bool tc_supported(const ts_actor_critic_desc& d) {
