@@ -153,7 +153,8 @@ __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
     s.dof = o;  o += kRows * kMaxAct * 4;  // dOut in fp32 [r][a]
     s.act = o;  o += kRows * kMaxAct * 4;  // actions of the tile
     s.rowv = o; o += 4 * kRows * 4;        // adv, ret, logp_old, v_s
-    s.red = o;  o += 64 * 4;
+    s.red = o;  o += 256 * 4;              // [0,12) per-warp sums, [64,80) 1/var, [80,96) log sigma + log sqrt(2 pi),
+                                           // [128,256) per-warp column sums of (dmu, dlogstd)
     s.total = o;
     return s;
 }
@@ -181,6 +182,29 @@ __device__ __forceinline__ void stage_chunks(uint8_t* sm0, const Mat& M, int row
     }
 }
 
+// Split form of stage_chunks for matrices with at most one task per thread: issue the 8 loads of the
+// thread's chunk now (chunk_load), convert + store later (chunk_store), so that the loads of several
+// matrices are in flight together.
+template <class RowPtrF>
+__device__ __forceinline__ void chunk_load(int rows, int cols, int cols_pad, RowPtrF&& rowptr, float (&v)[8]) {
+    const int nch = cols_pad >> 3;
+    const int sh = nch == 8 ? 3 : (nch == 4 ? 2 : 1);
+    const int task = threadIdx.x;
+    const int r = task >> sh, ch = task & (nch - 1);
+    const float* src = task < rows * nch ? rowptr(r) : (const float*)nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = 8 * ch + j;
+        v[j] = (src != nullptr && k < cols) ? __ldg(src + k) : 0.0f;
+    }
+}
+__device__ __forceinline__ void chunk_store(uint8_t* sm0, const Mat& M, int rows, int cols_pad, const float (&v)[8]) {
+    const int nch = cols_pad >> 3;
+    const int sh = nch == 8 ? 3 : (nch == 4 ? 2 : 1);
+    const int task = threadIdx.x;
+    if (task < rows * nch) store_chunk8(sm0, M, task >> sh, 8 * (task & (nch - 1)), v);
+}
+
 // Global -> shared staging with U loads in flight per thread (the loads are independent of the
 // stores, so batching them hides the L2 / HBM latency that a load-store-load-store loop exposes).
 template <int U, class LoadF, class StoreF>
@@ -204,11 +228,22 @@ __device__ __forceinline__ void staged_loop(int n, LoadF&& ld, StoreF&& st) {
 __device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const float* __restrict__ params, const NetG& g,
                               int obs_dim, int out_dim) {
     const int tid = threadIdx.x;
-    stage_chunks(sm0, S.W1, H, obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * obs_dim; });
-    stage_chunks(sm0, S.W2, H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; });
-    stage_chunks(sm0, S.W3, NO, H, H, [&](int a) { return a < out_dim ? params + g.w3 + (int64_t)a * H : (const float*)nullptr; });
     float* w3f = reinterpret_cast<float*>(sm + S.w3f);
-    for (int e = tid; e < kMaxAct * H; e += kThreads) w3f[e] = (e >> 6) < out_dim ? __ldg(params + g.w3 + e) : 0.0f;
+    {   // <= one chunk per thread and matrix (H = 64, KXP <= 32, 512 threads): all loads first
+        float v1[8], v2[8], v3[8], vf[2];
+        chunk_load(H, obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * obs_dim; }, v1);
+        chunk_load(H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; }, v2);
+        chunk_load(NO, H, H, [&](int a) { return a < out_dim ? params + g.w3 + (int64_t)a * H : (const float*)nullptr; }, v3);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = tid + u * kThreads;
+            vf[u] = (e >> 6) < out_dim ? __ldg(params + g.w3 + e) : 0.0f;
+        }
+        chunk_store(sm0, S.W1, H, S.KXP, v1);
+        chunk_store(sm0, S.W2, H, H, v2);
+        chunk_store(sm0, S.W3, NO, H, v3);
+        w3f[tid] = vf[0]; w3f[tid + kThreads] = vf[1];
+    }
     float* b1 = reinterpret_cast<float*>(sm + S.b1);
     float* b2 = reinterpret_cast<float*>(sm + S.b2);
     float* b3 = reinterpret_cast<float*>(sm + S.b3);
@@ -216,7 +251,13 @@ __device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const fl
     for (int e = tid; e < H; e += kThreads) { b1[e] = __ldg(params + g.b1 + e); b2[e] = __ldg(params + g.b2 + e); }
     if (tid < kMaxAct) {
         b3[tid] = tid < out_dim ? __ldg(params + g.b3 + tid) : 0.0f;
-        ls[tid] = (tid < out_dim && g.ls >= 0) ? __ldg(params + g.ls + tid) : 0.0f;
+        const float l = (tid < out_dim && g.ls >= 0) ? __ldg(params + g.ls + tid) : 0.0f;
+        ls[tid] = l;
+        // per-dimension constants of the diagonal Gaussian, once per CTA instead of once per row
+        float* gs = reinterpret_cast<float*>(sm + S.red) + 64;
+        const float sigma = expf(l);
+        gs[tid] = 1.0f / (sigma * sigma);
+        gs[16 + tid] = logf(sigma) + 0.9189385332046727f;
     }
 }
 
@@ -301,38 +342,83 @@ __device__ __forceinline__ void write_dout_row(uint8_t* sm, uint8_t* sm0, const 
     store_chunk8(sm0, S.DO, r, 8, dv + 8);
 }
 
-// weight-gradient accumulators (M = 64: row o = 16*q + lane for lane < 16) -> the CTA's partial row
-__device__ __forceinline__ void red_rows(uint32_t tmem, uint32_t col, int ncols, float* __restrict__ grad, int64_t base,
-                                         int64_t row_stride, int valid_cols) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// The partial row is private to the CTA: the first tile of a CTA stores, later tiles read-modify-write.
+__device__ __forceinline__ void out_acc(float* p, float v, bool first) { *p = first ? v : *p + v; }
+
+// Weight-gradient accumulators (TMEM, M = 64: row o = 16 q + lane for lane < 16) -> the CTA's partial
+// gradient row.  A lane owns a ROW of an accumulator, so direct stores would touch one 32-byte sector
+// per value (measured: 4-8 us per net).  The tile is transposed through shared memory instead (the H1
+// operand is dead after the last MMA; padded leading dimensions keep both sides bank-conflict free) and
+// written out with consecutive threads on consecutive addresses.
+constexpr int kLdW2 = H + 1, kLdW1 = 33, kScrW2 = 0, kScrW1 = kScrW2 + H * kLdW2, kScrW3 = kScrW1 + H * kLdW1,
+              kScrB1 = kScrW3 + NO * kLdW2, kScrB2 = kScrB1 + H, kScrEnd = kScrB2 + H;
+static_assert(kScrEnd * 4 <= 3 * kRows * H * 2, "gradient scratch must fit in the H1 operand");
+__device__ __forceinline__ void grad_out(uint8_t* sm0, const Smem& S, uint32_t tmem, const NetG& g, int obs_dim, int out_dim,
+                                         float* __restrict__ grad, bool first) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cq = warp >> 2;
-    // the four warps of a sub-partition take 8-column slabs round-robin
-    for (int c0 = 8 * cq; c0 < ncols; c0 += 32) {
-        float v[8];
-        umma::tmem_ld8(tmem + ((32u * q) << 16) + col + c0, v);
-        if (lane < 16) {
-            const int o = 16 * q + lane;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (c0 + j < valid_cols) atomicAdd(grad + base + (int64_t)o * row_stride + c0 + j, v[j]);
-        }
-    }
-}
-// transposed variant for dW3^T [k][a] -> grad W3[a][k]
-__device__ __forceinline__ void red_w3(uint32_t tmem, uint32_t col, float* __restrict__ grad, int64_t base, int out_dim) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, cq = warp >> 2;
-    if (cq >= NO / 8) return;      // warp-uniform
+    float* scr = reinterpret_cast<float*>(sm0 + S.H1.base);
+    const uint32_t t0 = tmem + ((32u * q) << 16);
+    const int o = 16 * q + lane;
     float v[8];
-    umma::tmem_ld8(tmem + ((32u * q) << 16) + col + 8 * cq, v);
-    if (lane < 16) {
-        const int k = 16 * q + lane;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int a = 8 * cq + j;
-            if (a < out_dim) atomicAdd(grad + base + (int64_t)a * H + k, v[j]);
+    for (int c0 = 0; c0 < H; c0 += 32) {                  // dW2 [o][i]
+        umma::tmem_ld8(t0 + cDW2 + c0 + 8 * cq, v);
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) scr[kScrW2 + o * kLdW2 + c0 + 8 * cq + j] = v[j];
         }
     }
+    if (8 * cq < S.KXP) {                                  // dW1 [o][i]   (warp-uniform)
+        umma::tmem_ld8(t0 + cDW1 + 8 * cq, v);
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) scr[kScrW1 + o * kLdW1 + 8 * cq + j] = v[j];
+        }
+    }
+    if (cq < NO / 8) {                                     // dW3^T [k][a] -> [a][k]
+        umma::tmem_ld8(t0 + cDW3 + 8 * cq, v);
+        if (lane < 16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) scr[kScrW3 + (8 * cq + j) * kLdW2 + o] = v[j];
+        }
+    } else {                                               // db2 (cq == 2), db1 (cq == 3): column 0 of the ones-GEMM
+        umma::tmem_ld8(t0 + (cq == 2 ? cDB2 : cDB1), v);
+        if (lane < 16) scr[(cq == 2 ? kScrB2 : kScrB1) + o] = v[0];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < H * H / kThreads; ++u) {
+        const int e = tid + u * kThreads;
+        out_acc(grad + g.w2 + e, scr[kScrW2 + (e >> 6) * kLdW2 + (e & (H - 1))], first);
+    }
+    if (lane < obs_dim) {
+#pragma unroll
+        for (int r = warp; r < H; r += kThreads / 32)
+            out_acc(grad + g.w1 + (int64_t)r * obs_dim + lane, scr[kScrW1 + r * kLdW1 + lane], first);
+    }
+    if (warp < out_dim) {
+        out_acc(grad + g.w3 + warp * H + lane, scr[kScrW3 + warp * kLdW2 + lane], first);
+        out_acc(grad + g.w3 + warp * H + 32 + lane, scr[kScrW3 + warp * kLdW2 + 32 + lane], first);
+    }
+    if (tid < H) out_acc(grad + g.b1 + tid, scr[kScrB1 + tid], first);
+    else if (tid < 2 * H) out_acc(grad + g.b2 + tid - H, scr[kScrB2 + tid - H], first);
+}
+
+// Sum 32 per-lane values over the warp with 31 shuffles; lane j returns the total of v[j].
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int n = 16; n >= 1; n >>= 1) {
+        const bool upper = (lane & n) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = upper ? v[i] : v[i + n];
+            const float keep = upper ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
 }
 
 // forward of one trunk: X -> H1 -> H2 -> head accumulator D3 (TMEM); h1 / h2 of the thread's
@@ -349,7 +435,7 @@ __device__ __forceinline__ void trunk_forward(uint8_t* sm, uint8_t* sm0, const S
 // backward of one trunk given dOut (S.DO / dof); writes all weight and bias gradients of the net
 __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, Pipe& pipe,
                                                const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad,
-                                               const float (&h1)[kCols], const float (&h2)[kCols]) {
+                                               const float (&h1)[kCols], const float (&h2)[kCols], bool first) {
     pipe.run([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });      // dW3^T = H2^T dOut
     tstamp(16);
     epi_head_input_grad(sm, sm0, S, out_dim, h2);
@@ -367,11 +453,7 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
         gemm_colsum(tmem + cDB1, S.H1, S.ONES, S.ONES_RS);                            // db1 = dZ1^T 1
     });
     tstamp(20);
-    red_w3(tmem, cDW3, grad, g.w3, out_dim);
-    red_rows(tmem, cDW2, H, grad, g.w2, H, H);
-    red_rows(tmem, cDB2, 8, grad, g.b2, 1, 1);
-    red_rows(tmem, cDW1, S.KXP, grad, g.w1, obs_dim, obs_dim);
-    red_rows(tmem, cDB1, 8, grad, g.b1, 1, 1);
+    grad_out(sm0, S, tmem, g, obs_dim, out_dim, grad, first);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -423,7 +505,17 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // this CTA's private partial-gradient row: no cross-CTA atomics, folded by clip_adam_kernel
     float* __restrict__ grad = partials + (size_t)blockIdx.x * (size_t)(d.n_params + TS_PPO_GRAD_EXTRA);
-    for (int64_t i = tid; i < d.n_params + TS_PPO_GRAD_EXTRA; i += kThreads) grad[i] = 0.0f;
+    __shared__ int32_t s_row[kRows];
+    const int64_t tiles0 = (hi - lo + kRows - 1) / kRows;
+    if ((int64_t)blockIdx.x >= tiles0)     // idle CTA (launchers never create one): an all-zero partial row
+        for (int64_t i = tid; i < d.n_params + TS_PPO_GRAD_EXTRA; i += kThreads) grad[i] = 0.0f;
+    auto prefetch_rows = [&](int64_t t) {   // dataset row of every tile row, one step ahead of its use
+        if (tid < kRows && t < tiles0) {
+            const int64_t pos = lo + t * kRows + tid;
+            s_row[tid] = pos < hi ? (perm ? __ldg(perm + pos) : (int32_t)pos) : 0;
+        }
+    };
+    prefetch_rows(blockIdx.x);
     const uint32_t sbase = umma::smem_u32(sm);
     uint8_t* sm0 = sm - sbase;     // so that (sm0 + shared_address) is the generic pointer
     const Smem S = make_smem(d.obs_dim, sbase);
@@ -450,28 +542,29 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
     const int64_t tiles = (hi - lo + kRows - 1) / kRows;
     tstamp(0);
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const bool first = (t == (int64_t)blockIdx.x);     // first tile of this CTA: gradients are stored, not added
         const int64_t pos0 = lo + t * kRows;
         const int nrows = (int)tsb::imin((int64_t)kRows, hi - pos0);
-        // ---- tile inputs -----------------------------------------------------------------------
-        stage_chunks(sm0, S.X, kRows, d.obs_dim, S.KXP, [&](int r) {
-            if (r >= nrows) return (const float*)nullptr;
-            const int64_t row = perm ? (int64_t)__ldg(perm + pos0 + r) : pos0 + r;
-            return obs + row * d.obs_dim;
-        });
-        if (tid < kRows) {   // the row's actions (fp32, read back by the same thread in the loss epilogue)
-            const int64_t row = (tid < nrows) ? (perm ? (int64_t)__ldg(perm + pos0 + tid) : pos0 + tid) : -1;
+        // ---- tile inputs: row ids (prefetched), then every gather of the tile in flight together -------
+        {
+            float xv[8], av[kMaxAct], rv[4] = {0.f, 0.f, 0.f, 0.f};
+            chunk_load(kRows, d.obs_dim, S.KXP, [&](int r) {
+                return r < nrows ? obs + (int64_t)s_row[r] * d.obs_dim : (const float*)nullptr;
+            }, xv);
+            if (tid < kRows) {
+                const int64_t row = tid < nrows ? (int64_t)s_row[tid] : -1;
 #pragma unroll
-            for (int a = 0; a < kMaxAct; ++a) actt[tid * kMaxAct + a] = (row >= 0 && a < A) ? __ldg(act + row * A + a) : 0.0f;
-        }
-        if (tid < kRows) {
-            float a_ = 0.f, r_ = 0.f, l_ = 0.f, v_ = 0.f;
-            if (tid < nrows) {
-                const int64_t row = perm ? (int64_t)perm[pos0 + tid] : pos0 + tid;
-                a_ = __ldg(adv + row); r_ = __ldg(ret + row); l_ = __ldg(logp_old + row); v_ = __ldg(v_s + row);
+                for (int a = 0; a < kMaxAct; ++a) av[a] = (row >= 0 && a < A) ? __ldg(act + row * A + a) : 0.0f;
+                if (row >= 0) { rv[0] = __ldg(adv + row); rv[1] = __ldg(ret + row); rv[2] = __ldg(logp_old + row); rv[3] = __ldg(v_s + row); }
             }
-            rowv[tid] = a_; rowv[kRows + tid] = r_; rowv[2 * kRows + tid] = l_; rowv[3 * kRows + tid] = v_;
+            chunk_store(sm0, S.X, kRows, S.KXP, xv);
+            if (tid < kRows) {
+#pragma unroll
+                for (int a = 0; a < kMaxAct; a += 4)
+                    *reinterpret_cast<float4*>(actt + tid * kMaxAct + a) = make_float4(av[a], av[a + 1], av[a + 2], av[a + 3]);
+                rowv[tid] = rv[0]; rowv[kRows + tid] = rv[1]; rowv[2 * kRows + tid] = rv[2]; rowv[3 * kRows + tid] = rv[3];
+            }
         }
-        if (tid < 64) red[tid] = 0.0f;
 
         // ================= critic ================================================================
         float h1[kCols], h2[kCols];
@@ -492,13 +585,14 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
             }
             write_dout_row(sm, sm0, S, tid, dv);
             const float sdv = warp_sum(dv[0]);
-            if (lane == 0) atomicAdd(red + 0, sdv);            // db3 (critic)
+            if (lane == 0) red[warp] = sdv;                    // db3 (critic), one slot per warp
         }
         tstamp(4);
-        trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2);
+        trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2, first);
         tstamp(5);
         __syncthreads();
-        if (tid == 0) { atomicAdd(grad + gc.b3, red[0]); red[0] = 0.0f; }
+        if (tid == 0) out_acc(grad + gc.b3, (red[0] + red[1]) + (red[2] + red[3]), first);
+        prefetch_rows(t + gridDim.x);
 
         // ================= actor =================================================================
         stage_weights(sm, sm0, S, params, ga, d.obs_dim, A);
@@ -508,63 +602,61 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
         float clip_row = 0.0f;
         if (tid < kRows) {
             const int r = tid;
-            float v16[16], dv[kMaxAct], dls[kMaxAct];
+            float v16[16], cs[32];      // cs[a] = d/d mu_a, cs[16 + a] = d/d logstd_a
             umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
             const float* b3 = reinterpret_cast<const float*>(sm + S.b3);
-            const float* ls = reinterpret_cast<const float*>(sm + S.ls);
+            const float* inv_var = red + 64;      // 1 / sigma^2
+            const float* logc = red + 80;         // log sigma + log sqrt(2 pi)
             float lp = 0.0f;
-            float sig[kMaxAct], diff[kMaxAct];
+            float diff[kMaxAct], d2v[kMaxAct];
 #pragma unroll
-            for (int a = 0; a < kMaxAct; ++a) {
-                sig[a] = 1.0f; diff[a] = 0.0f;
-                if (a < A) {
-                    sig[a] = expf(ls[a]);
-                    const float mu = v16[a] + b3[a];
-                    const float x = actt[r * kMaxAct + a];
-                    diff[a] = x - mu;
-                    lp += ppo::normal_logp_term(x, mu, sig[a]);
+            for (int a4 = 0; a4 < kMaxAct; a4 += 4) {
+                const float4 x4 = *reinterpret_cast<const float4*>(actt + r * kMaxAct + a4);
+                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int a = a4 + u;
+                    diff[a] = 0.0f; d2v[a] = 0.0f;
+                    if (a < A) {     // warp-uniform
+                        diff[a] = xs[u] - (v16[a] + b3[a]);
+                        d2v[a] = diff[a] * diff[a] * inv_var[a];
+                        lp += fmaf(-0.5f, d2v[a], -logc[a]);   // log N(x; mu, sigma)
+                    }
                 }
             }
             float gl = 0.0f;
             if (r < nrows) ppo::actor_row(sc, lp, rowv[2 * kRows + r], rowv[r], clip_row, gl);
 #pragma unroll
             for (int a = 0; a < kMaxAct; ++a) {
-                const float var = sig[a] * sig[a];
-                dv[a] = a < A ? gl * diff[a] / var : 0.0f;                       // d/d mu
-                dls[a] = a < A ? gl * (diff[a] * diff[a] / var - 1.0f) : 0.0f;  // d/d logstd
+                cs[a] = a < A ? gl * diff[a] * inv_var[a] : 0.0f;
+                cs[16 + a] = a < A ? gl * (d2v[a] - 1.0f) : 0.0f;
             }
-            write_dout_row(sm, sm0, S, r, dv);
-            // column sums over the 32 rows of this warp: db3[a] and dlogstd[a]
-#pragma unroll
-            for (int a = 0; a < kMaxAct; ++a) {
-                if (a < A) {
-                    const float s1 = warp_sum(dv[a]), s2 = warp_sum(dls[a]);
-                    if (lane == 0) { atomicAdd(red + 16 + a, s1); atomicAdd(red + 32 + a, s2); }
-                }
-            }
+            write_dout_row(sm, sm0, S, r, cs);
+            // column sums over the 32 rows of this warp: lane a <- db3[a], lane 16 + a <- dlogstd[a]
+            red[128 + 32 * warp + lane] = warp_transpose_sum32(cs);
         }
         tstamp(8);
-        trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2);
+        trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2, first);
         tstamp(9);
 
         // ================= loss sums + small gradients ===========================================
         const float s_clip = warp_sum(tid < kRows ? clip_row : 0.0f);
         const float s_vf = warp_sum(tid < kRows ? vf_row : 0.0f);
-        if (lane == 0 && tid < kRows) { atomicAdd(red + 1, s_clip); atomicAdd(red + 2, s_vf); }
+        if (lane == 0 && tid < kRows) { red[4 + warp] = s_clip; red[8 + warp] = s_vf; }
         __syncthreads();
         if (tid < A) {
-            atomicAdd(grad + ga.b3 + tid, red[16 + tid]);
-            atomicAdd(grad + ga.ls + tid, red[32 + tid] - sc.ent_coef * sc.inv_b * (float)nrows);
+            const float* cw = red + 128 + tid;
+            out_acc(grad + ga.b3 + tid, (cw[0] + cw[32]) + (cw[64] + cw[96]), first);
+            out_acc(grad + ga.ls + tid, (cw[16] + cw[48]) + (cw[80] + cw[112]) - sc.ent_coef * sc.inv_b * (float)nrows, first);
         }
         if (tid == 0) {
-            const float* ls = reinterpret_cast<const float*>(sm + S.ls);
-            float ent = 0.0f;
-            for (int a = 0; a < A; ++a) ent += 1.4189385332046727f + logf(expf(ls[a]));
+            float ent = 0.0f;     // entropy of the diagonal Gaussian: sum_a (0.5 + log sqrt(2 pi) + log sigma_a)
+            for (int a = 0; a < A; ++a) ent += 0.5f + red[80 + a];
             float* ex = grad + d.n_params;
-            atomicAdd(ex + 0, red[1]);
-            atomicAdd(ex + 1, red[2]);
-            atomicAdd(ex + 2, ent * (float)nrows);
-            atomicAdd(ex + 3, (float)nrows);
+            out_acc(ex + 0, (red[4] + red[5]) + (red[6] + red[7]), first);
+            out_acc(ex + 1, (red[8] + red[9]) + (red[10] + red[11]), first);
+            out_acc(ex + 2, ent * (float)nrows, first);
+            out_acc(ex + 3, (float)nrows, first);
         }
         __syncthreads();
     }
