@@ -259,7 +259,8 @@ int ts_clip_adam_step(float* params, float* grad, const float* partials, int32_t
  * rewritten when recompute_adv).  stats: repeat*n_mb rows.  rms_state as in ts_gae (nullable
  * when return_scaling is off).  v_next_tmp: N f32 scratch.  gae_ws: ts_gae_workspace_bytes(N).
  * grad: n_params + TS_PPO_GRAD_EXTRA floats scratch; partials: ts_ppo_partial_rows() rows of the
- * same width.  adv_tmp: double[2]+float[2] bytes.
+ * same width.  adv_tmp: 32 + 8 * n_minibatch bytes of zero-initialised scratch (double[2] sums, float[2] moments,
+ * then one (mean, std) float pair per minibatch).
  */
 int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, float* exp_avg_sq,
                   int64_t* step_count, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,

@@ -115,7 +115,7 @@ class PPO(ActorCriticOnPolicyAlgorithm):
         else:
             perms = None
 
-        adv_tmp = self._buf("adv_tmp", 32, torch.uint8)
+        adv_tmp = self._buf("adv_tmp", 32 + 8 * n_mb, torch.uint8)
         adv_tmp.zero_()
         bounds_c = (C.c_int64 * (2 * n_mb))(*[x for b in bounds for x in b])
 

@@ -680,6 +680,34 @@ __global__ void adv_finalize_kernel(double* __restrict__ sums, int64_t n, float*
     sums[0] = 0.0; sums[1] = 0.0;
 }
 
+// mean / unbiased std of the advantages of EVERY minibatch of one pass (one CTA per minibatch, fixed
+// summation order): out[2 m] = mean, out[2 m + 1] = std                       (ppo.py:181-183)
+__global__ void __launch_bounds__(1024) epoch_adv_moments_kernel(const float* __restrict__ adv, const int32_t* __restrict__ perm,
+                                                                 int64_t lo0, int64_t mb_size, int64_t end, int n_mb,
+                                                                 float* __restrict__ out) {
+    __shared__ double s1[32], s2[32];
+    const int m = blockIdx.x;
+    const int64_t lo = lo0 + (int64_t)m * mb_size, hi = m == n_mb - 1 ? end : lo + mb_size;
+    double a = 0.0, b = 0.0;
+    for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+        const double v = adv[perm ? (int64_t)perm[p] : p];
+        a += v; b += v * v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { a += tsb::shfl_xor_f64(a, off); b += tsb::shfl_xor_f64(b, off); }
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { x += s1[w]; y += s2[w]; }
+        const int64_t n = hi - lo;
+        const double mean = x / (double)n;
+        double var = (y - x * mean) / (double)(n > 1 ? n - 1 : 1);
+        if (var < 0.0) var = 0.0;
+        out[2 * m] = (float)mean; out[2 * m + 1] = (float)sqrt(var);
+    }
+}
+
 // ---- keyed bijection of [0, n): balanced Feistel on an even number of bits + cycle walking ----
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
@@ -745,11 +773,11 @@ int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const
                        float* grad, cudaStream_t st);
 int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
                       const float* in1, float* out1, int64_t n, cudaStream_t st);
-int launch_ppo_step_tc(float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
-                       const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
-                       const int32_t* perm, int64_t lo, int64_t hi, const float* adv_moments, float* partials,
-                       float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count, float* stats_row,
-                       cudaStream_t st);
+int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
+                        const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
+                        const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, const float* adv_moments,
+                        float* partials, float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count,
+                        float* stats, cudaStream_t st);
 static bool simt_forced() {
     static const bool f = [] { const char* e = getenv("TS_B200_FORCE_SIMT"); return e && e[0] == '1'; }();
     return f;
@@ -883,6 +911,14 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
     const bool fused = tsb::tc_supported(*desc) && !tsb::simt_forced() && !no_fuse;
     double* adv_sums = static_cast<double*>(adv_tmp);
     float* adv_mom = adv_tmp ? reinterpret_cast<float*>(adv_sums + 2) : nullptr;
+    float* epoch_mom = adv_tmp ? reinterpret_cast<float*>(static_cast<uint8_t*>(adv_tmp) + 32) : nullptr;
+    // Batch.split minibatches are regular: [m * size, (m + 1) * size) with the remainder merged into the last one
+    bool regular = n_minibatch > 0;
+    const int64_t lo0 = n_minibatch > 0 ? bounds[0] : 0, mb_size = n_minibatch > 0 ? bounds[1] - bounds[0] : 0;
+    for (int m = 0; m < n_minibatch && regular; ++m) {
+        regular = bounds[2 * m] == lo0 + (int64_t)m * mb_size && bounds[2 * m + 1] > bounds[2 * m] &&
+                  (m == n_minibatch - 1 || bounds[2 * m + 1] == lo0 + (int64_t)(m + 1) * mb_size);
+    }
     for (int r = 0; r < repeat; ++r) {
         if (recompute_adv && r > 0) {    // ppo.py:174-178 -> a2c.py:115-153
             TS_REQUIRE(obs_next && rew && v_next_tmp && gae_ws, "ts_ppo_update: recompute needs obs_next/rew/scratch");
@@ -891,17 +927,29 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
                                lam, rms_state, rms_eps, nullptr, adv, returns, TS_F32, gae_ws, stream)) return e;
         }
         const int32_t* pr = perm ? perm + (int64_t)r * N : nullptr;
+        float* rows = stats + (int64_t)r * n_minibatch * TS_PPO_STATS_STRIDE;
+        if (fused && regular) {   // ONE persistent launch for all optimiser steps of this pass
+            const int64_t end = bounds[2 * n_minibatch - 1];
+            if (hp->advantage_normalization) {
+                epoch_adv_moments_kernel<<<n_minibatch, 1024, 0, tsb::as_stream(stream)>>>(adv, pr, lo0, mb_size, end, n_minibatch, epoch_mom);
+                if (int e = tsb::check_launch("ts_ppo_update(adv moments)")) return e;
+            }
+            if (int e = tsb::launch_ppo_epoch_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo0, mb_size, end,
+                                                 n_minibatch, hp->advantage_normalization ? epoch_mom : nullptr, partials, grad,
+                                                 exp_avg, exp_avg_sq, step_count, rows, tsb::as_stream(stream))) return e;
+            continue;
+        }
         for (int m = 0; m < n_minibatch; ++m) {
             const int64_t lo = bounds[2 * m], hi = bounds[2 * m + 1];
             if (hp->advantage_normalization) {
                 if (int e = ts_minibatch_adv_sums(adv, pr, lo, hi, adv_sums, stream)) return e;
                 if (int e = ts_adv_moments_finalize(adv_sums, hi - lo, adv_mom, stream)) return e;
             }
-            float* row = stats + ((int64_t)r * n_minibatch + m) * TS_PPO_STATS_STRIDE;
-            if (fused) {   // one launch per optimiser step
-                if (int e = tsb::launch_ppo_step_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo, hi,
-                                                    adv_mom, partials, grad, exp_avg, exp_avg_sq, step_count, row,
-                                                    tsb::as_stream(stream))) return e;
+            float* row = rows + (int64_t)m * TS_PPO_STATS_STRIDE;
+            if (fused) {   // irregular bounds: one launch per optimiser step
+                if (int e = tsb::launch_ppo_epoch_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo, hi - lo, hi,
+                                                     1, adv_mom, partials, grad, exp_avg, exp_avg_sq, step_count, row,
+                                                     tsb::as_stream(stream))) return e;
                 continue;
             }
             int32_t n_part = 0;

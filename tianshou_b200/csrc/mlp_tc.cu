@@ -45,8 +45,9 @@ constexpr uint32_t kTmemCols = 512;
 // %globaltimer at each phase boundary; read back with ts_tc_timeline().
 __device__ unsigned long long g_tc_timeline[32];
 __device__ int g_tc_timeline_on = 0;
+__device__ int g_tc_timeline_gate = 1;      // written and read by CTA 0 / thread 0 only: which step is recorded
 __device__ __forceinline__ void tstamp(int slot) {
-    if (g_tc_timeline_on && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (g_tc_timeline_on && blockIdx.x == 0 && threadIdx.x == 0 && g_tc_timeline_gate) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_tc_timeline[slot] = t;
@@ -185,7 +186,9 @@ __device__ __forceinline__ void stage_chunks(uint8_t* sm0, const Mat& M, int row
 // Split form of stage_chunks for matrices with at most one task per thread: issue the 8 loads of the
 // thread's chunk now (chunk_load), convert + store later (chunk_store), so that the loads of several
 // matrices are in flight together.
-template <class RowPtrF>
+// COHERENT: read through L2 (ld.global.cg) -- required for the parameters, which other CTAs rewrite
+// between the steps of the persistent epoch kernel (the read-only / L1 path could return stale lines).
+template <bool COHERENT = false, class RowPtrF>
 __device__ __forceinline__ void chunk_load(int rows, int cols, int cols_pad, RowPtrF&& rowptr, float (&v)[8]) {
     const int nch = cols_pad >> 3;
     const int sh = nch == 8 ? 3 : (nch == 4 ? 2 : 1);
@@ -195,7 +198,7 @@ __device__ __forceinline__ void chunk_load(int rows, int cols, int cols_pad, Row
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = 8 * ch + j;
-        v[j] = (src != nullptr && k < cols) ? __ldg(src + k) : 0.0f;
+        v[j] = (src != nullptr && k < cols) ? (COHERENT ? __ldcg(src + k) : __ldg(src + k)) : 0.0f;
     }
 }
 __device__ __forceinline__ void chunk_store(uint8_t* sm0, const Mat& M, int rows, int cols_pad, const float (&v)[8]) {
@@ -225,19 +228,19 @@ __device__ __forceinline__ void staged_loop(int n, LoadF&& ld, StoreF&& st) {
 }
 
 // stage one network's weights: bf16x3 blocked copies for the tensor core + fp32 side copies
-__device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const float* __restrict__ params, const NetG& g,
+__device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const float* params, const NetG& g,
                               int obs_dim, int out_dim) {
     const int tid = threadIdx.x;
     float* w3f = reinterpret_cast<float*>(sm + S.w3f);
     {   // <= one chunk per thread and matrix (H = 64, KXP <= 32, 512 threads): all loads first
         float v1[8], v2[8], v3[8], vf[2];
-        chunk_load(H, obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * obs_dim; }, v1);
-        chunk_load(H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; }, v2);
-        chunk_load(NO, H, H, [&](int a) { return a < out_dim ? params + g.w3 + (int64_t)a * H : (const float*)nullptr; }, v3);
+        chunk_load<true>(H, obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * obs_dim; }, v1);
+        chunk_load<true>(H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; }, v2);
+        chunk_load<true>(NO, H, H, [&](int a) { return a < out_dim ? params + g.w3 + (int64_t)a * H : (const float*)nullptr; }, v3);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int e = tid + u * kThreads;
-            vf[u] = (e >> 6) < out_dim ? __ldg(params + g.w3 + e) : 0.0f;
+            vf[u] = (e >> 6) < out_dim ? __ldcg(params + g.w3 + e) : 0.0f;
         }
         chunk_store(sm0, S.W1, H, S.KXP, v1);
         chunk_store(sm0, S.W2, H, H, v2);
@@ -248,10 +251,10 @@ __device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const fl
     float* b2 = reinterpret_cast<float*>(sm + S.b2);
     float* b3 = reinterpret_cast<float*>(sm + S.b3);
     float* ls = reinterpret_cast<float*>(sm + S.ls);
-    for (int e = tid; e < H; e += kThreads) { b1[e] = __ldg(params + g.b1 + e); b2[e] = __ldg(params + g.b2 + e); }
+    for (int e = tid; e < H; e += kThreads) { b1[e] = __ldcg(params + g.b1 + e); b2[e] = __ldcg(params + g.b2 + e); }
     if (tid < kMaxAct) {
-        b3[tid] = tid < out_dim ? __ldg(params + g.b3 + tid) : 0.0f;
-        const float l = (tid < out_dim && g.ls >= 0) ? __ldg(params + g.ls + tid) : 0.0f;
+        b3[tid] = tid < out_dim ? __ldcg(params + g.b3 + tid) : 0.0f;
+        const float l = (tid < out_dim && g.ls >= 0) ? __ldcg(params + g.ls + tid) : 0.0f;
         ls[tid] = l;
         // per-dimension constants of the diagonal Gaussian, once per CTA instead of once per row
         float* gs = reinterpret_cast<float*>(sm + S.red) + 64;
@@ -462,67 +465,80 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// State of the in-kernel grid barriers of the fused step (self-resetting; launches are stream-ordered
-// and every CTA of the grid is resident: grid <= #SMs, 1 CTA / SM).
-__device__ unsigned int g_step_bar[2] = {0u, 0u};
-__device__ unsigned int g_step_depart = 0u;
-__device__ double g_step_ss = 0.0;
+// State of the in-kernel grid barriers of the fused epoch kernel (self-resetting; launches are
+// stream-ordered and every CTA of the grid is resident: cooperative launch, 1 CTA / SM).
+__device__ unsigned int g_ep_arrive = 0u;
+__device__ unsigned int g_ep_depart = 0u;
+__device__ double g_ep_ss[2] = {0.0, 0.0};
 
-struct AdamArgs {     // optimiser half of the fused single-GPU step
+struct AdamArgs {     // optimiser half of the fused single-GPU path
     float* params_w;
     float* grad_scratch;   // n_params + TS_PPO_GRAD_EXTRA folded values (loss sums are read back from here)
     float* exp_avg;
     float* exp_avg_sq;
     int64_t* step_count;
-    float* stats_row;
+    float* stats;          // one row of TS_PPO_STATS_STRIDE floats per minibatch (nullable)
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned int* ctr) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        while (*((volatile unsigned int*)ctr) < gridDim.x) {}
-        __threadfence();
+struct GridBarrier {   // monotonic counter: the k-th use waits for k * gridDim.x arrivals
+    unsigned int target;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            __threadfence();
+            atomicAdd(&g_ep_arrive, 1u);
+            while (*((volatile unsigned int*)&g_ep_arrive) < target) {}
+            __threadfence();
+        }
+        __syncthreads();
     }
-    __syncthreads();
-}
+};
 
-// FUSE_ADAM = false: write this CTA's partial gradient row and stop (multi-GPU: fold + all-reduce +
-// ts_clip_adam_step follow).  FUSE_ADAM = true: after a grid barrier every CTA folds its slice of the
-// gradient over all partial rows, a second barrier publishes the global sum of squares, then the slice's
-// clip + Adam update is applied in place -- the whole optimiser step is ONE launch.
-template <bool FUSE_ADAM>
-__global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
-    const float* __restrict__ params, const ts_actor_critic_desc d, const ts_ppo_hparams hp,
+struct TileIn { float xv[8]; float av[kMaxAct]; float rv[4]; };   // one thread's share of a tile's gathers
+
+// The minibatches of one launch are [lo0 + m * mb_size, lo0 + (m + 1) * mb_size) for m < n_mb - 1 and
+// [lo0 + (n_mb - 1) * mb_size, end) for the last one (Batch.split with merge_last, batch.py:1196-1215).
+//
+// EPOCH = false: n_mb = 1; write this CTA's partial gradient row and stop (multi-GPU: fold + all-reduce
+// + ts_clip_adam_step follow).
+// EPOCH = true: persistent over the n_mb optimiser steps of one pass over the rollout.  Per step: tile
+// forward/backward -> grid barrier -> every CTA folds its slice of the gradient over the partial rows ->
+// barrier (global sum of squares) -> clip + Adam on the slice -> barrier (parameters visible).  The gathers
+// of the NEXT minibatch's tile are issued before the first barrier and land while the CTA waits.
+template <bool EPOCH>
+__global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
+    const float* params, const ts_actor_critic_desc d, const ts_ppo_hparams hp,
     const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ adv,
     const float* __restrict__ ret, const float* __restrict__ logp_old, const float* __restrict__ v_s,
-    const int32_t* __restrict__ perm, int64_t lo, int64_t hi, int64_t global_rows,
+    const int32_t* __restrict__ perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, int64_t global_rows,
     const float* __restrict__ adv_moments, float* __restrict__ partials, const AdamArgs opt) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_bar;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // this CTA's private partial-gradient row: no cross-CTA atomics, folded by clip_adam_kernel
-    float* __restrict__ grad = partials + (size_t)blockIdx.x * (size_t)(d.n_params + TS_PPO_GRAD_EXTRA);
     __shared__ int32_t s_row[kRows];
-    const int64_t tiles0 = (hi - lo + kRows - 1) / kRows;
-    if ((int64_t)blockIdx.x >= tiles0)     // idle CTA (launchers never create one): an all-zero partial row
-        for (int64_t i = tid; i < d.n_params + TS_PPO_GRAD_EXTRA; i += kThreads) grad[i] = 0.0f;
-    auto prefetch_rows = [&](int64_t t) {   // dataset row of every tile row, one step ahead of its use
-        if (tid < kRows && t < tiles0) {
-            const int64_t pos = lo + t * kRows + tid;
-            s_row[tid] = pos < hi ? (perm ? __ldg(perm + pos) : (int32_t)pos) : 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int P = (int)gridDim.x;
+    const int64_t width = d.n_params + TS_PPO_GRAD_EXTRA;
+    // this CTA's private partial-gradient row: no cross-CTA atomics
+    float* __restrict__ grad = partials + (size_t)blockIdx.x * (size_t)width;
+    auto mb_lo = [&](int m) { return lo0 + (int64_t)m * mb_size; };
+    auto mb_hi = [&](int m) { return m == n_mb - 1 ? end : lo0 + (int64_t)(m + 1) * mb_size; };
+    auto mb_tiles = [&](int m) { return (mb_hi(m) - mb_lo(m) + kRows - 1) / kRows; };
+    auto prefetch_rows = [&](int m, int64_t t) {   // dataset row of every tile row, ahead of its use
+        if (tid < kRows) {
+            const int64_t pos = mb_lo(m) + t * kRows + tid;
+            s_row[tid] = pos < mb_hi(m) ? (perm ? __ldg(perm + pos) : (int32_t)pos) : 0;
         }
     };
-    prefetch_rows(blockIdx.x);
+    if ((int64_t)blockIdx.x < mb_tiles(0)) prefetch_rows(0, blockIdx.x);
     const uint32_t sbase = umma::smem_u32(sm);
     uint8_t* sm0 = sm - sbase;     // so that (sm0 + shared_address) is the generic pointer
     const Smem S = make_smem(d.obs_dim, sbase);
     const int A = d.act_dim;
-    const ppo::Scalars sc = ppo::make_scalars(hp, global_rows, adv_moments);
     const NetG ga{d.a_w1, d.a_b1, d.a_w2, d.a_b2, d.a_w3, d.a_b3, d.a_logstd};
     const NetG gc{d.c_w1, d.c_b1, d.c_w2, d.c_b2, d.c_w3, d.c_b3, -1};
+    const int64_t step0 = EPOCH ? *opt.step_count : 0;
 
     if (warp == 0) umma::tmem_alloc(&s_tmem, kTmemCols);
     if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
@@ -535,161 +551,187 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
     Pipe pipe{&s_bar, 0u};
+    GridBarrier gbar{0u};
     float* rowv = reinterpret_cast<float*>(sm + S.rowv);
     float* red = reinterpret_cast<float*>(sm + S.red);
     float* actt = reinterpret_cast<float*>(sm + S.act);
 
-    const int64_t tiles = (hi - lo + kRows - 1) / kRows;
+    // every gather of a tile in flight together (rows from s_row) ...
+    auto load_inputs = [&](int nrows, TileIn& in) {
+        chunk_load(kRows, d.obs_dim, S.KXP, [&](int r) {
+            return r < nrows ? obs + (int64_t)s_row[r] * d.obs_dim : (const float*)nullptr;
+        }, in.xv);
+        if (tid < kRows) {
+            const int64_t row = tid < nrows ? (int64_t)s_row[tid] : -1;
+#pragma unroll
+            for (int a = 0; a < kMaxAct; ++a) in.av[a] = (row >= 0 && a < A) ? __ldg(act + row * A + a) : 0.0f;
+            in.rv[0] = in.rv[1] = in.rv[2] = in.rv[3] = 0.0f;
+            if (row >= 0) { in.rv[0] = __ldg(adv + row); in.rv[1] = __ldg(ret + row); in.rv[2] = __ldg(logp_old + row); in.rv[3] = __ldg(v_s + row); }
+        }
+    };
+    // ... and their conversion into the tile's operands
+    auto store_inputs = [&](const TileIn& in) {
+        chunk_store(sm0, S.X, kRows, S.KXP, in.xv);
+        if (tid < kRows) {
+#pragma unroll
+            for (int a = 0; a < kMaxAct; a += 4)
+                *reinterpret_cast<float4*>(actt + tid * kMaxAct + a) = make_float4(in.av[a], in.av[a + 1], in.av[a + 2], in.av[a + 3]);
+            rowv[tid] = in.rv[0]; rowv[kRows + tid] = in.rv[1]; rowv[2 * kRows + tid] = in.rv[2]; rowv[3 * kRows + tid] = in.rv[3];
+        }
+    };
+
+    bool staged = false;        // the tile's inputs were already stored by the previous step's prefetch
     tstamp(0);
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const bool first = (t == (int64_t)blockIdx.x);     // first tile of this CTA: gradients are stored, not added
-        const int64_t pos0 = lo + t * kRows;
-        const int nrows = (int)tsb::imin((int64_t)kRows, hi - pos0);
-        // ---- tile inputs: row ids (prefetched), then every gather of the tile in flight together -------
-        {
-            float xv[8], av[kMaxAct], rv[4] = {0.f, 0.f, 0.f, 0.f};
-            chunk_load(kRows, d.obs_dim, S.KXP, [&](int r) {
-                return r < nrows ? obs + (int64_t)s_row[r] * d.obs_dim : (const float*)nullptr;
-            }, xv);
-            if (tid < kRows) {
-                const int64_t row = tid < nrows ? (int64_t)s_row[tid] : -1;
-#pragma unroll
-                for (int a = 0; a < kMaxAct; ++a) av[a] = (row >= 0 && a < A) ? __ldg(act + row * A + a) : 0.0f;
-                if (row >= 0) { rv[0] = __ldg(adv + row); rv[1] = __ldg(ret + row); rv[2] = __ldg(logp_old + row); rv[3] = __ldg(v_s + row); }
+    for (int m = 0; m < n_mb; ++m) {
+        const int64_t lo = mb_lo(m), hi = mb_hi(m);
+        const int64_t tiles = (hi - lo + kRows - 1) / kRows;
+        const ppo::Scalars sc = ppo::make_scalars(hp, EPOCH ? hi - lo : global_rows, adv_moments ? adv_moments + 2 * m : nullptr);
+        if (blockIdx.x == 0 && tid == 0) g_tc_timeline_gate = (n_mb == 1 || m == n_mb - 2);   // a step WITH barrier 3
+        tstamp(22);
+        bool next_rows_ready = false;   // s_row holds the rows of this CTA's first tile of minibatch m + 1
+        for (int64_t t = blockIdx.x; t < tiles; t += P) {
+            const bool first = (t == (int64_t)blockIdx.x);     // first tile of this CTA: gradients are stored, not added
+            const int nrows = (int)tsb::imin((int64_t)kRows, hi - (lo + t * kRows));
+            if (!staged) {
+                TileIn in;
+                load_inputs(nrows, in);
+                store_inputs(in);
             }
-            chunk_store(sm0, S.X, kRows, S.KXP, xv);
-            if (tid < kRows) {
-#pragma unroll
-                for (int a = 0; a < kMaxAct; a += 4)
-                    *reinterpret_cast<float4*>(actt + tid * kMaxAct + a) = make_float4(av[a], av[a + 1], av[a + 2], av[a + 3]);
-                rowv[tid] = rv[0]; rowv[kRows + tid] = rv[1]; rowv[2 * kRows + tid] = rv[2]; rowv[3 * kRows + tid] = rv[3];
-            }
-        }
+            staged = false;
 
-        // ================= critic ================================================================
-        float h1[kCols], h2[kCols];
-        tstamp(1);
-        stage_weights(sm, sm0, S, params, gc, d.obs_dim, 1);
-        tstamp(2);
-        trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
-        tstamp(3);
-        float vf_row = 0.0f;
-        if (tid < kRows) {
-            float v16[16], dv[kMaxAct];
-            umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
+            // ================= critic ================================================================
+            float h1[kCols], h2[kCols];
+            tstamp(1);
+            stage_weights(sm, sm0, S, params, gc, d.obs_dim, 1);
+            tstamp(2);
+            trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
+            tstamp(3);
+            float vf_row = 0.0f;
+            if (tid < kRows) {
+                float v16[16], dv[kMaxAct];
+                umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
 #pragma unroll
-            for (int a = 0; a < kMaxAct; ++a) dv[a] = 0.0f;
-            if (tid < nrows) {
-                const float value = v16[0] + reinterpret_cast<const float*>(sm + S.b3)[0];
-                ppo::critic_row(sc, value, rowv[kRows + tid], rowv[3 * kRows + tid], vf_row, dv[0]);
+                for (int a = 0; a < kMaxAct; ++a) dv[a] = 0.0f;
+                if (tid < nrows) {
+                    const float value = v16[0] + reinterpret_cast<const float*>(sm + S.b3)[0];
+                    ppo::critic_row(sc, value, rowv[kRows + tid], rowv[3 * kRows + tid], vf_row, dv[0]);
+                }
+                write_dout_row(sm, sm0, S, tid, dv);
+                const float sdv = warp_sum(dv[0]);
+                if (lane == 0) red[warp] = sdv;                    // db3 (critic), one slot per warp
             }
-            write_dout_row(sm, sm0, S, tid, dv);
-            const float sdv = warp_sum(dv[0]);
-            if (lane == 0) red[warp] = sdv;                    // db3 (critic), one slot per warp
-        }
-        tstamp(4);
-        trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2, first);
-        tstamp(5);
-        __syncthreads();
-        if (tid == 0) out_acc(grad + gc.b3, (red[0] + red[1]) + (red[2] + red[3]), first);
-        prefetch_rows(t + gridDim.x);
+            tstamp(4);
+            trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2, first);
+            tstamp(5);
+            __syncthreads();
+            if (tid == 0) out_acc(grad + gc.b3, (red[0] + red[1]) + (red[2] + red[3]), first);
+            // row ids of this CTA's next tile (s_row was consumed by load_inputs long ago)
+            if (t + P < tiles) prefetch_rows(m, t + P);
+            else if (m + 1 < n_mb && (int64_t)blockIdx.x < mb_tiles(m + 1)) { prefetch_rows(m + 1, blockIdx.x); next_rows_ready = true; }
 
-        // ================= actor =================================================================
-        stage_weights(sm, sm0, S, params, ga, d.obs_dim, A);
-        tstamp(6);
-        trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
-        tstamp(7);
-        float clip_row = 0.0f;
-        if (tid < kRows) {
-            const int r = tid;
-            float v16[16], cs[32];      // cs[a] = d/d mu_a, cs[16 + a] = d/d logstd_a
-            umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
-            const float* b3 = reinterpret_cast<const float*>(sm + S.b3);
-            const float* inv_var = red + 64;      // 1 / sigma^2
-            const float* logc = red + 80;         // log sigma + log sqrt(2 pi)
-            float lp = 0.0f;
-            float diff[kMaxAct], d2v[kMaxAct];
+            // ================= actor =================================================================
+            stage_weights(sm, sm0, S, params, ga, d.obs_dim, A);
+            tstamp(6);
+            trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
+            tstamp(7);
+            float clip_row = 0.0f;
+            if (tid < kRows) {
+                const int r = tid;
+                float v16[16], cs[32];      // cs[a] = d/d mu_a, cs[16 + a] = d/d logstd_a
+                umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
+                const float* b3 = reinterpret_cast<const float*>(sm + S.b3);
+                const float* inv_var = red + 64;      // 1 / sigma^2
+                const float* logc = red + 80;         // log sigma + log sqrt(2 pi)
+                float lp = 0.0f;
+                float diff[kMaxAct], d2v[kMaxAct];
 #pragma unroll
-            for (int a4 = 0; a4 < kMaxAct; a4 += 4) {
-                const float4 x4 = *reinterpret_cast<const float4*>(actt + r * kMaxAct + a4);
-                const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+                for (int a4 = 0; a4 < kMaxAct; a4 += 4) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(actt + r * kMaxAct + a4);
+                    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int a = a4 + u;
-                    diff[a] = 0.0f; d2v[a] = 0.0f;
-                    if (a < A) {     // warp-uniform
-                        diff[a] = xs[u] - (v16[a] + b3[a]);
-                        d2v[a] = diff[a] * diff[a] * inv_var[a];
-                        lp += fmaf(-0.5f, d2v[a], -logc[a]);   // log N(x; mu, sigma)
+                    for (int u = 0; u < 4; ++u) {
+                        const int a = a4 + u;
+                        diff[a] = 0.0f; d2v[a] = 0.0f;
+                        if (a < A) {     // warp-uniform
+                            diff[a] = xs[u] - (v16[a] + b3[a]);
+                            d2v[a] = diff[a] * diff[a] * inv_var[a];
+                            lp += fmaf(-0.5f, d2v[a], -logc[a]);   // log N(x; mu, sigma)
+                        }
                     }
                 }
-            }
-            float gl = 0.0f;
-            if (r < nrows) ppo::actor_row(sc, lp, rowv[2 * kRows + r], rowv[r], clip_row, gl);
+                float gl = 0.0f;
+                if (r < nrows) ppo::actor_row(sc, lp, rowv[2 * kRows + r], rowv[r], clip_row, gl);
 #pragma unroll
-            for (int a = 0; a < kMaxAct; ++a) {
-                cs[a] = a < A ? gl * diff[a] * inv_var[a] : 0.0f;
-                cs[16 + a] = a < A ? gl * (d2v[a] - 1.0f) : 0.0f;
+                for (int a = 0; a < kMaxAct; ++a) {
+                    cs[a] = a < A ? gl * diff[a] * inv_var[a] : 0.0f;
+                    cs[16 + a] = a < A ? gl * (d2v[a] - 1.0f) : 0.0f;
+                }
+                write_dout_row(sm, sm0, S, r, cs);
+                // column sums over the 32 rows of this warp: lane a <- db3[a], lane 16 + a <- dlogstd[a]
+                red[128 + 32 * warp + lane] = warp_transpose_sum32(cs);
             }
-            write_dout_row(sm, sm0, S, r, cs);
-            // column sums over the 32 rows of this warp: lane a <- db3[a], lane 16 + a <- dlogstd[a]
-            red[128 + 32 * warp + lane] = warp_transpose_sum32(cs);
-        }
-        tstamp(8);
-        trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2, first);
-        tstamp(9);
+            tstamp(8);
+            trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2, first);
+            tstamp(9);
 
-        // ================= loss sums + small gradients ===========================================
-        const float s_clip = warp_sum(tid < kRows ? clip_row : 0.0f);
-        const float s_vf = warp_sum(tid < kRows ? vf_row : 0.0f);
-        if (lane == 0 && tid < kRows) { red[4 + warp] = s_clip; red[8 + warp] = s_vf; }
-        __syncthreads();
-        if (tid < A) {
-            const float* cw = red + 128 + tid;
-            out_acc(grad + ga.b3 + tid, (cw[0] + cw[32]) + (cw[64] + cw[96]), first);
-            out_acc(grad + ga.ls + tid, (cw[16] + cw[48]) + (cw[80] + cw[112]) - sc.ent_coef * sc.inv_b * (float)nrows, first);
+            // ================= loss sums + small gradients ===========================================
+            const float s_clip = warp_sum(tid < kRows ? clip_row : 0.0f);
+            const float s_vf = warp_sum(tid < kRows ? vf_row : 0.0f);
+            if (lane == 0 && tid < kRows) { red[4 + warp] = s_clip; red[8 + warp] = s_vf; }
+            __syncthreads();
+            if (tid < A) {
+                const float* cw = red + 128 + tid;
+                out_acc(grad + ga.b3 + tid, (cw[0] + cw[32]) + (cw[64] + cw[96]), first);
+                out_acc(grad + ga.ls + tid, (cw[16] + cw[48]) + (cw[80] + cw[112]) - sc.ent_coef * sc.inv_b * (float)nrows, first);
+            }
+            if (tid == 0) {
+                float ent = 0.0f;     // entropy of the diagonal Gaussian: sum_a (0.5 + log sqrt(2 pi) + log sigma_a)
+                for (int a = 0; a < A; ++a) ent += 0.5f + red[80 + a];
+                float* ex = grad + d.n_params;
+                out_acc(ex + 0, (red[4] + red[5]) + (red[6] + red[7]), first);
+                out_acc(ex + 1, (red[8] + red[9]) + (red[10] + red[11]), first);
+                out_acc(ex + 2, ent * (float)nrows, first);
+                out_acc(ex + 3, (float)nrows, first);
+            }
+            __syncthreads();
         }
-        if (tid == 0) {
-            float ent = 0.0f;     // entropy of the diagonal Gaussian: sum_a (0.5 + log sqrt(2 pi) + log sigma_a)
-            for (int a = 0; a < A; ++a) ent += 0.5f + red[80 + a];
-            float* ex = grad + d.n_params;
-            out_acc(ex + 0, (red[4] + red[5]) + (red[6] + red[7]), first);
-            out_acc(ex + 1, (red[8] + red[9]) + (red[10] + red[11]), first);
-            out_acc(ex + 2, ent * (float)nrows, first);
-            out_acc(ex + 3, (float)nrows, first);
-        }
-        __syncthreads();
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+        if (!EPOCH) break;
 
-    if (FUSE_ADAM) {
-        // ---- gradient fold over the partial rows of all CTAs (fixed order, L2 resident) ------------
+        // ---- optimiser half of the step --------------------------------------------------------------
         __shared__ float s_part[4][128];
         __shared__ double s_red[4];
         __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
-        const int P = (int)gridDim.x;
-        const int64_t width = d.n_params + TS_PPO_GRAD_EXTRA;
+        const int Pm = (int)tsb::imin((int64_t)P, tiles);           // partial rows written for this minibatch
         const int64_t slice = (width + P - 1) / P;
         const int64_t i0 = (int64_t)blockIdx.x * slice;
         const int64_t i1 = tsb::imin(i0 + slice, width);
         const int e = tid & 127, q = tid >> 7;
-        const int64_t step = *opt.step_count + 1;
+        const int64_t step = step0 + m + 1;
+        double* ss_cur = &g_ep_ss[m & 1];
         tstamp(10);
-        grid_barrier(&g_step_bar[0]);                               // every partial row is complete
+        // gathers of this CTA's tile of the next minibatch: in flight across the barrier
+        TileIn pin;
+        const bool pre = (m + 1 < n_mb) && (int64_t)blockIdx.x < mb_tiles(m + 1);
+        int nrows_next = 0;
+        if (pre) {
+            if (!next_rows_ready) { prefetch_rows(m + 1, blockIdx.x); __syncthreads(); }
+            nrows_next = (int)tsb::imin((int64_t)kRows, mb_hi(m + 1) - (mb_lo(m + 1) + (int64_t)blockIdx.x * kRows));
+            load_inputs(nrows_next, pin);
+        }
+        gbar.sync();                                                // every partial row is complete
         tstamp(11);
+        if (pre) { store_inputs(pin); staged = true; }
         double ss = 0.0;
         for (int64_t c = i0; c < i1; c += 128) {
             const int64_t i = c + e;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (i < i1) {
                 int p = q;
-                for (; p + 28 < P; p += 32) {
+                for (; p + 28 < Pm; p += 32) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) acc[u] += __ldcg(partials + (int64_t)(p + 4 * u) * width + i);
                 }
-                for (; p < P; p += 4) acc[0] += __ldcg(partials + (int64_t)p * width + i);
+                for (; p < Pm; p += 4) acc[0] += __ldcg(partials + (int64_t)p * width + i);
             }
             s_part[q][e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
             __syncthreads();
@@ -707,11 +749,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
         }
         __syncthreads();
         tstamp(12);
-        if (tid == 0) atomicAdd(&g_step_ss, (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]));
-        grid_barrier(&g_step_bar[1]);
-        tstamp(13);                               // global sum of squares is complete
+        if (tid == 0) atomicAdd(ss_cur, (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]));
+        gbar.sync();                                                // global sum of squares is complete
+        tstamp(13);
         if (tid == 0) {
-            const float total_norm = (float)sqrt(*((volatile double*)&g_step_ss));
+            const float total_norm = (float)sqrt(*((volatile double*)ss_cur));
             float coef = 1.0f;
             if (hp.max_grad_norm > 0.0) {   // torch.nn.utils.clip_grad_norm_
                 coef = (float)hp.max_grad_norm / (total_norm + 1e-6f);
@@ -722,6 +764,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
             const double bc2 = 1.0 - pow(hp.beta2, (double)step);
             s_step_size = (float)(hp.lr / bc1);
             s_bc2_sqrt = (float)sqrt(bc2);
+            if (blockIdx.x == 0) g_ep_ss[(m + 1) & 1] = 0.0;       // next step's accumulator (idle until barrier 3)
         }
         __syncthreads();
         const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
@@ -731,32 +774,39 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_tc_kernel(
             float g = opt.grad_scratch[i] * coef;
             float pv = opt.params_w[i];
             if (wd != 0.0f) g = fmaf(wd, pv, g);
-            float m = opt.exp_avg[i], v = opt.exp_avg_sq[i];
-            m = m + w1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
+            float mm = opt.exp_avg[i], v = opt.exp_avg_sq[i];
+            mm = mm + w1 * (g - mm);                    // exp_avg.lerp_(grad, 1 - beta1)
             v = v * beta2 + w2 * g * g;                 // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
             const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
-            pv = pv - step_size * (m / denom);          // addcdiv_(exp_avg, denom, -step_size)
-            opt.exp_avg[i] = m; opt.exp_avg_sq[i] = v; opt.params_w[i] = pv;
+            pv = pv - step_size * (mm / denom);         // addcdiv_(exp_avg, denom, -step_size)
+            opt.exp_avg[i] = mm; opt.exp_avg_sq[i] = v; opt.params_w[i] = pv;
         }
-        if (tid == 0) {
-            if (blockIdx.x == 0) {
-                const float* ex = opt.grad_scratch + d.n_params;
-                const float e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
-                const float rows = e3 > 0.0f ? e3 : 1.0f;
-                const float clip_loss = -e0 / rows, vf_loss = e1 / rows, ent_loss = e2 / rows;
-                if (opt.stats_row) {
-                    float* sr = opt.stats_row;
-                    sr[0] = clip_loss + (float)hp.vf_coef * vf_loss - (float)hp.ent_coef * ent_loss;
-                    sr[1] = clip_loss; sr[2] = vf_loss; sr[3] = ent_loss;
-                    sr[4] = s_norm; sr[5] = e3; sr[6] = 0.0f; sr[7] = 0.0f;
-                }
-                *opt.step_count = step;
+        if (tid == 0 && blockIdx.x == 0) {
+            // the folded loss sums were written by the owner of the last slice before barrier 2
+            const float* ex = opt.grad_scratch + d.n_params;
+            const float e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
+            const float rows = e3 > 0.0f ? e3 : 1.0f;
+            const float clip_loss = -e0 / rows, vf_loss = e1 / rows, ent_loss = e2 / rows;
+            if (opt.stats) {
+                float* sr = opt.stats + (int64_t)m * TS_PPO_STATS_STRIDE;
+                sr[0] = clip_loss + (float)hp.vf_coef * vf_loss - (float)hp.ent_coef * ent_loss;
+                sr[1] = clip_loss; sr[2] = vf_loss; sr[3] = ent_loss;
+                sr[4] = s_norm; sr[5] = e3; sr[6] = 0.0f; sr[7] = 0.0f;
             }
-            tstamp(14);
-            if (atomicAdd(&g_step_depart, 1u) == gridDim.x - 1) {
-                g_step_bar[0] = 0u; g_step_bar[1] = 0u; g_step_depart = 0u; g_step_ss = 0.0;
-                __threadfence();
-            }
+        }
+        tstamp(14);
+        if (m + 1 < n_mb) gbar.sync();                              // updated parameters visible to every CTA
+        tstamp(15);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+    if (EPOCH && tid == 0) {
+        if (blockIdx.x == 0) *opt.step_count = step0 + n_mb;
+        __threadfence();
+        if (atomicAdd(&g_ep_depart, 1u) == gridDim.x - 1) {
+            g_ep_arrive = 0u; g_ep_depart = 0u; g_ep_ss[0] = 0.0; g_ep_ss[1] = 0.0;
+            __threadfence();
         }
     }
 }
@@ -896,42 +946,52 @@ bool tc_supported(const ts_actor_critic_desc& d) {
     return d.hidden == H && d.obs_dim >= 1 && d.obs_dim <= 32 && d.act_dim >= 1 && d.act_dim <= kMaxAct;
 }
 
+static int configure_ppo_smem(size_t smem) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        TS_CUDA(cudaFuncSetAttribute(ppo_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TS_CUDA(cudaFuncSetAttribute(ppo_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    return 0;
+}
+
 int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
                        const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
                        const int32_t* perm, int64_t lo, int64_t hi, int64_t global_rows, const float* adv_moments,
                        float* grad, cudaStream_t st) {
     const size_t smem = make_smem(d.obs_dim, 0).total;
-    static size_t configured = 0;
-    if (smem > configured) {
-        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (int e = configure_ppo_smem(smem)) return e;
     const int64_t tiles = (hi - lo + kRows - 1) / kRows;
     const unsigned grid = (unsigned)imin(tiles, num_sms());
-    ppo_grad_tc_kernel<false><<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi,
-                                                            global_rows, adv_moments, grad, AdamArgs{});
+    ppo_tc_kernel<false><<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi - lo, hi, 1,
+                                                       global_rows, adv_moments, grad, AdamArgs{});
     return check_launch("ts_ppo_grad(tc)");
 }
 
-// one whole optimiser step (minibatch fwd/bwd + gradient fold + clip + Adam + stats) in ONE launch
-int launch_ppo_step_tc(float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
-                       const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
-                       const int32_t* perm, int64_t lo, int64_t hi, const float* adv_moments, float* partials,
-                       float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count, float* stats_row,
-                       cudaStream_t st) {
+// n_mb consecutive optimiser steps (minibatch fwd/bwd + gradient fold + clip + Adam + stats each) in ONE
+// cooperative launch: every CTA is resident (grid <= #SMs, 1 CTA / SM), so the in-kernel grid barriers are safe.
+int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_ppo_hparams& hp, const float* obs,
+                        const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
+                        const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, const float* adv_moments,
+                        float* partials, float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count,
+                        float* stats, cudaStream_t st) {
     const size_t smem = make_smem(d.obs_dim, 0).total;
-    static size_t configured = 0;
-    if (smem > configured) {
-        TS_CUDA(cudaFuncSetAttribute(ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    const int64_t tiles = (hi - lo + kRows - 1) / kRows;
-    const unsigned grid = (unsigned)imin(tiles, num_sms());   // all CTAs co-resident (1 per SM): grid barriers are safe
-    const AdamArgs opt{params, grad_scratch, exp_avg, exp_avg_sq, step_count, stats_row};
-    ppo_grad_tc_kernel<true><<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi,
-                                                           hi - lo, adv_moments, partials, opt);
-    return check_launch("ts_ppo_step(tc)");
+    if (int e = configure_ppo_smem(smem)) return e;
+    const int64_t last = end - (lo0 + (int64_t)(n_mb - 1) * mb_size);
+    const int64_t widest = n_mb > 1 ? (mb_size > last ? mb_size : last) : last;
+    const unsigned grid = (unsigned)imin((widest + kRows - 1) / kRows, num_sms());
+    const AdamArgs opt{params, grad_scratch, exp_avg, exp_avg_sq, step_count, stats};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int64_t zero = 0;
+    TS_CUDA(cudaLaunchKernelEx(&cfg, ppo_tc_kernel<true>, (const float*)params, d, hp, obs, act, adv, ret, logp_old, v_s, perm,
+                               lo0, mb_size, end, n_mb, zero, adv_moments, partials, opt));
+    return check_launch("ts_ppo_epoch(tc)");
 }
 
 int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
