@@ -223,6 +223,11 @@ typedef struct ts_ppo_hparams {
  * over all ranks (the mean's denominator); adv_moments: device float[2] = {mean, std} when
  * advantage_normalization, else NULL.  perm may be NULL (identity). */
 int32_t ts_ppo_partial_rows(void);
+
+/* Bytes of the optional `weight_image` scratch of ts_ppo_update: both networks' weights pre-split into the
+ * bf16x3 tensor-core operand layout, so that a CTA stages a network with one bulk copy.  0 when the network
+ * shape is not covered by the tensor-core kernels (pass NULL then). */
+int64_t ts_ppo_weight_image_bytes(const ts_actor_critic_desc* desc);
 int ts_ppo_grad(const float* params, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
                 const float* obs, const float* act, const float* adv, const float* ret,
                 const float* logp_old, const float* v_s, const int32_t* perm, int64_t lo,
@@ -260,7 +265,8 @@ int ts_clip_adam_step(float* params, float* grad, const float* partials, int32_t
  * when return_scaling is off).  v_next_tmp: N f32 scratch.  gae_ws: ts_gae_workspace_bytes(N).
  * grad: n_params + TS_PPO_GRAD_EXTRA floats scratch; partials: ts_ppo_partial_rows() rows of the
  * same width.  adv_tmp: 32 + 8 * n_minibatch bytes of zero-initialised scratch (double[2] sums, float[2] moments,
- * then one (mean, std) float pair per minibatch).
+ * then one (mean, std) float pair per minibatch).  weight_image: ts_ppo_weight_image_bytes(desc) bytes of scratch
+ * (nullable: the kernels then gather + split the weights themselves every step); rebuilt from `params` on entry.
  */
 int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, float* exp_avg_sq,
                   int64_t* step_count, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
@@ -270,7 +276,7 @@ int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, f
                   float* v_next_tmp, int64_t N, const int32_t* perm, int32_t repeat,
                   const int64_t* bounds /* host */, int32_t n_minibatch, int32_t recompute_adv,
                   double gamma, double lam, double* rms_state, double rms_eps, void* gae_ws,
-                  void* adv_tmp, float* stats, ts_stream_t stream);
+                  void* adv_tmp, void* weight_image, float* stats, ts_stream_t stream);
 
 /* Device-side minibatch order (opt-in alternative to np.random.permutation, batch.py:1209):
  * out[r*n + i] = pi_r(i), pi_r a keyed bijection of [0,n) (cycle-walking Feistel/Philox). */

@@ -81,14 +81,14 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_clip_adam_step": [_P, _P, _P, _I32, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams), _P, _P],
     "ts_ppo_update": [_P, _P, _P, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams),
                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32,
-                      C.POINTER(_I64), _I32, _I32, _D, _D, _P, _D, _P, _P, _P, _P],
+                      C.POINTER(_I64), _I32, _I32, _D, _D, _P, _D, _P, _P, _P, _P, _P],
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
     "ts_narrow_i64_i32": [_P, _I64, _P, _P],
     "ts_tc_timeline": [_I32, _P],
     "ts_umma_selftest": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 OTHER_SYMBOLS = ["ts_version", "ts_last_error", "ts_launch_count", "ts_reset_launch_count",
-                 "ts_gae_workspace_bytes", "ts_ppo_partial_rows"]
+                 "ts_gae_workspace_bytes", "ts_ppo_partial_rows", "ts_ppo_weight_image_bytes"]
 
 _lib: C.CDLL | None = None
 
@@ -116,6 +116,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ts_gae_workspace_bytes.argtypes = [_I64]
     lib.ts_gae_workspace_bytes.restype = C.c_size_t
     lib.ts_ppo_partial_rows.restype = C.c_int32
+    lib.ts_ppo_weight_image_bytes.argtypes = [C.POINTER(ActorCriticDesc)]
+    lib.ts_ppo_weight_image_bytes.restype = C.c_int64
     if path is None:
         _lib = lib
     return lib

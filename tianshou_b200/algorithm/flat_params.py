@@ -108,6 +108,7 @@ class FlatParams:
         self.exp_avg = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.exp_avg_sq = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self.weight_image: torch.Tensor | None = None   # set by the algorithm (needs the network descriptor)
         self._ptrs: list[int] = []
         self.adopt()
 

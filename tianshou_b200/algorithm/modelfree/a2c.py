@@ -77,6 +77,12 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
                 f"actor/critic live on {dev}; tianshou_b200 has no CPU path -- move them to a CUDA device first")
         check_gaussian_dist_fn(self.policy.dist_fn, self._desc.act_dim, dev)
         self._flat = FlatParams(plist, dev, GRAD_EXTRA)
+        # scratch for the pre-split (bf16x3) weight image of the tensor-core update kernel; None -> the
+        # kernels gather + split the weights themselves (networks the tensor-core path does not cover)
+        import ctypes as _C
+        from ..._cabi import load_library
+        nbytes = int(load_library().ts_ppo_weight_image_bytes(_C.byref(self._desc)))
+        self._flat.weight_image = torch.zeros(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
         if self._world_size() > 1:  # replicas start bit-identical
             from ...parallel import broadcast_params_
             broadcast_params_(self._flat.flat)

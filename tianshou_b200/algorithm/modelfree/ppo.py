@@ -128,7 +128,7 @@ class PPO(ActorCriticOnPolicyAlgorithm):
                  ptr(self._buf("v_next", N, torch.float32)), N, ptr(perm_rows), nrep, bounds_c, n_mb,
                  int(recompute), float(self.gamma), float(self.gae_lambda),
                  ptr(self._rms_device()) if self.return_scaling else None, float(self._eps),
-                 ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(stats[r0 * n_mb:]), stream_ptr(dev))
+                 ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(f.weight_image), ptr(stats[r0 * n_mb:]), stream_ptr(dev))
 
         if single_call:
             run_repeats(perms, 0, repeat, self.recompute_adv)

@@ -777,7 +777,8 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
                         const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
                         const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, const float* adv_moments,
                         float* partials, float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count,
-                        float* stats, cudaStream_t st);
+                        float* stats, void* weight_image, cudaStream_t st);
+int64_t weight_image_bytes(const ts_actor_critic_desc& d);
 static bool simt_forced() {
     static const bool f = [] { const char* e = getenv("TS_B200_FORCE_SIMT"); return e && e[0] == '1'; }();
     return f;
@@ -862,6 +863,10 @@ extern "C" int ts_adv_moments_finalize(const double* sums, int64_t global_rows, 
 
 extern "C" int32_t ts_ppo_partial_rows(void) { return tsb::num_sms(); }
 
+extern "C" int64_t ts_ppo_weight_image_bytes(const ts_actor_critic_desc* desc) {
+    return desc ? tsb::weight_image_bytes(*desc) : 0;
+}
+
 extern "C" int ts_grad_reduce(const float* partials, int32_t n_partials, const ts_actor_critic_desc* desc,
                               float* grad, ts_stream_t stream) {
     TS_REQUIRE(partials && desc && grad && n_partials >= 0, "ts_grad_reduce: bad arguments");
@@ -903,7 +908,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
                              int64_t N, const int32_t* perm, int32_t repeat, const int64_t* bounds,
                              int32_t n_minibatch, int32_t recompute_adv, double gamma, double lam,
                              double* rms_state, double rms_eps, void* gae_ws, void* adv_tmp,
-                             float* stats, ts_stream_t stream) {
+                             void* weight_image, float* stats, ts_stream_t stream) {
     if (check_desc(desc, "ts_ppo_update")) return 2;
     TS_REQUIRE(hp && bounds && stats && partials && grad && repeat >= 0 && n_minibatch >= 0, "ts_ppo_update: bad arguments");
     TS_REQUIRE(!hp->advantage_normalization || adv_tmp, "ts_ppo_update: adv_tmp required");
@@ -936,7 +941,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
             }
             if (int e = tsb::launch_ppo_epoch_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo0, mb_size, end,
                                                  n_minibatch, hp->advantage_normalization ? epoch_mom : nullptr, partials, grad,
-                                                 exp_avg, exp_avg_sq, step_count, rows, tsb::as_stream(stream))) return e;
+                                                 exp_avg, exp_avg_sq, step_count, rows, weight_image, tsb::as_stream(stream))) return e;
             continue;
         }
         for (int m = 0; m < n_minibatch; ++m) {
@@ -949,7 +954,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
             if (fused) {   // irregular bounds: one launch per optimiser step
                 if (int e = tsb::launch_ppo_epoch_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo, hi - lo, hi,
                                                      1, adv_mom, partials, grad, exp_avg, exp_avg_sq, step_count, row,
-                                                     tsb::as_stream(stream))) return e;
+                                                     weight_image, tsb::as_stream(stream))) return e;
                 continue;
             }
             int32_t n_part = 0;

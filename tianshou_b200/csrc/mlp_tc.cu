@@ -129,6 +129,8 @@ struct Smem {   // byte offsets from the dynamic shared memory base (all multipl
     Mat X, H1, H2, DO, W1, W2, W3;
     uint32_t ONES, ONES_RS;
     uint32_t w3f, b1, b2, b3, ls, dof, rowv, red, act;
+    uint32_t wblk, wblk_bytes;   // the "weight block" W1 | W2 | W3 | w3f | b1 | b2 | b3 | ls: one contiguous range, the unit
+                                 // of the pre-split weight image in global memory (one bulk copy per network)
     uint32_t total;
 };
 __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
@@ -142,15 +144,17 @@ __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
     mat(s.H1, kRows, H);
     mat(s.H2, kRows, H);
     mat(s.DO, kRows, NO);
+    s.wblk = o;
     mat(s.W1, H, s.KXP);
     mat(s.W2, H, H);
     mat(s.W3, NO, H);
-    s.ONES = sbase + o; s.ONES_RS = 128u; o += mat_bytes(kRows, 8);
     s.w3f = o;  o += kMaxAct * H * 4;      // natural fp32 W3 [a][k] for the SIMT K=act GEMM
     s.b1 = o;   o += H * 4;
     s.b2 = o;   o += H * 4;
     s.b3 = o;   o += kMaxAct * 4;
     s.ls = o;   o += kMaxAct * 4;
+    s.wblk_bytes = o - s.wblk;             // multiple of 128
+    s.ONES = sbase + o; s.ONES_RS = 128u; o += mat_bytes(kRows, 8);
     s.dof = o;  o += kRows * kMaxAct * 4;  // dOut in fp32 [r][a]
     s.act = o;  o += kRows * kMaxAct * 4;  // actions of the tile
     s.rowv = o; o += 4 * kRows * 4;        // adv, ret, logp_old, v_s
@@ -262,6 +266,54 @@ __device__ void stage_weights(uint8_t* sm, uint8_t* sm0, const Smem& S, const fl
         gs[tid] = 1.0f / (sigma * sigma);
         gs[16 + tid] = logf(sigma) + 0.9189385332046727f;
     }
+}
+
+// ---- pre-split weight image --------------------------------------------------------------------------
+// Global-memory copy of both networks' weight blocks in exactly the shared-memory layout (bf16x3 blocked
+// operands + fp32 side copies; block 0 = critic, block 1 = actor), so that staging a network is ONE
+// cp.async.bulk instead of ~13 k scattered loads + splits per CTA and step.  Built by
+// weight_image_build_kernel; the Adam phase of the epoch kernel updates the entries of the parameters it
+// rewrites.  Padding (columns >= obs_dim, head rows >= out_dim) is zero and never touched.
+__device__ __forceinline__ void img_put(uint8_t* blk, uint32_t rel, uint32_t part, uint32_t RS, uint32_t r, uint32_t c, float x) {
+    uint32_t w0, w1, w2;
+    split3_pair(x, 0.0f, w0, w1, w2);
+    uint8_t* p = blk + rel + moff(r, c, RS);
+    *reinterpret_cast<uint16_t*>(p) = (uint16_t)w0;
+    *reinterpret_cast<uint16_t*>(p + part) = (uint16_t)w1;
+    *reinterpret_cast<uint16_t*>(p + 2 * part) = (uint16_t)w2;
+}
+__device__ __forceinline__ bool img_scatter_net(const Smem& S, uint32_t sbase, const NetG& g, int obs_dim, int out_dim,
+                                                int64_t i, float x, uint8_t* blk) {
+    const uint32_t w0 = sbase + S.wblk;       // Mat bases are shared addresses; the image uses block-relative offsets
+    int64_t o;
+    if ((o = i - g.w1) >= 0 && o < (int64_t)H * obs_dim) {
+        const uint32_t r = (uint32_t)o / (uint32_t)obs_dim, c = (uint32_t)o - r * (uint32_t)obs_dim;
+        img_put(blk, S.W1.base - w0, S.W1.part, S.W1.RS, r, c, x);
+        return true;
+    }
+    if ((o = i - g.w2) >= 0 && o < H * H) { img_put(blk, S.W2.base - w0, S.W2.part, S.W2.RS, (uint32_t)o >> 6, (uint32_t)o & 63u, x); return true; }
+    if ((o = i - g.w3) >= 0 && o < (int64_t)out_dim * H) {
+        img_put(blk, S.W3.base - w0, S.W3.part, S.W3.RS, (uint32_t)o >> 6, (uint32_t)o & 63u, x);
+        reinterpret_cast<float*>(blk + (S.w3f - S.wblk))[o] = x;
+        return true;
+    }
+    if ((o = i - g.b1) >= 0 && o < H) { reinterpret_cast<float*>(blk + (S.b1 - S.wblk))[o] = x; return true; }
+    if ((o = i - g.b2) >= 0 && o < H) { reinterpret_cast<float*>(blk + (S.b2 - S.wblk))[o] = x; return true; }
+    if ((o = i - g.b3) >= 0 && o < out_dim) { reinterpret_cast<float*>(blk + (S.b3 - S.wblk))[o] = x; return true; }
+    if (g.ls >= 0 && (o = i - g.ls) >= 0 && o < out_dim) { reinterpret_cast<float*>(blk + (S.ls - S.wblk))[o] = x; return true; }
+    return false;
+}
+__device__ __forceinline__ void img_scatter(const ts_actor_critic_desc& d, const Smem& S, uint32_t sbase, int64_t i, float x,
+                                            uint8_t* wimg) {
+    const NetG gc{d.c_w1, d.c_b1, d.c_w2, d.c_b2, d.c_w3, d.c_b3, -1};
+    if (img_scatter_net(S, sbase, gc, d.obs_dim, 1, i, x, wimg)) return;
+    const NetG ga{d.a_w1, d.a_b1, d.a_w2, d.a_b2, d.a_w3, d.a_b3, d.a_logstd};
+    img_scatter_net(S, sbase, ga, d.obs_dim, d.act_dim, i, x, wimg + S.wblk_bytes);
+}
+__global__ void weight_image_build_kernel(const float* __restrict__ params, const ts_actor_critic_desc d, uint8_t* __restrict__ wimg) {
+    const Smem S = make_smem(d.obs_dim, 0u);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n_params; i += (int64_t)gridDim.x * blockDim.x)
+        img_scatter(d, S, 0u, i, params[i], wimg);
 }
 
 struct Pipe {   // MMA issue / completion handshake
@@ -435,10 +487,13 @@ __device__ __forceinline__ void trunk_forward(uint8_t* sm, uint8_t* sm0, const S
     pipe.run([&] { gemm<H / 16>(tmem + cD3, 128, NO, S.H2, 0, S.W3, 0); });
 }
 
-// backward of one trunk given dOut (S.DO / dof); writes all weight and bias gradients of the net
+// backward of one trunk given dOut (S.DO / dof); writes all weight and bias gradients of the net.
+// `weights_dead()` is called (all threads) once nothing reads the network's weight block any more.
+template <class F>
 __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, Pipe& pipe,
                                                const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad,
-                                               const float (&h1)[kCols], const float (&h2)[kCols], bool first) {
+                                               const float (&h1)[kCols], const float (&h2)[kCols], bool first,
+                                               F&& weights_dead) {
     pipe.run([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });      // dW3^T = H2^T dOut
     tstamp(16);
     epi_head_input_grad(sm, sm0, S, out_dim, h2);
@@ -449,6 +504,7 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
         gemm<H / 16>(tmem + cDH1, 128, H, S.H2, 0, S.W2, 1);                          // dH1 = dZ2 W2
     });
     tstamp(18);
+    weights_dead();
     epi_dtanh(sm0, S.H1, tmem, cDH1, h1);                                             // H1 := dZ1
     tstamp(19);
     pipe.run([&] {
@@ -512,10 +568,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ adv,
     const float* __restrict__ ret, const float* __restrict__ logp_old, const float* __restrict__ v_s,
     const int32_t* __restrict__ perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, int64_t global_rows,
-    const float* __restrict__ adv_moments, float* __restrict__ partials, const AdamArgs opt) {
+    const float* __restrict__ adv_moments, float* __restrict__ partials, const AdamArgs opt, uint8_t* wimg /* nullable */) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_wbar;
     __shared__ int32_t s_row[kRows];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = (int)gridDim.x;
@@ -541,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     const int64_t step0 = EPOCH ? *opt.step_count : 0;
 
     if (warp == 0) umma::tmem_alloc(&s_tmem, kTmemCols);
-    if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
+    if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::mbar_init(&s_wbar, 1); umma::fence_mbar_init(); }
     {   // block of ones (bf16 1.0 = 0x3F80), blocked layout with 1 chunk per row
         uint32_t* ones = reinterpret_cast<uint32_t*>(sm0 + S.ONES);
         for (int e = tid; e < kRows * 8 / 2; e += kThreads) ones[e] = 0x3F803F80u;
@@ -552,6 +609,28 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     const uint32_t tmem = s_tmem;
     Pipe pipe{&s_bar, 0u};
     GridBarrier gbar{0u};
+    // Weight staging.  With a weight image: one bulk copy (TMA engine) per network, issued as early as the
+    // block is dead, completion on s_wbar.  Without: gather + split in the CTA (stage_weights).
+    uint32_t wphase = 0u;
+    bool critic_issued = false;
+    auto issue_weights = [&](int net) {   // every earlier access to the weight block is ordered before this call
+        if (wimg != nullptr && tid == 0) {
+            umma::fence_proxy_async_all();
+            umma::mbar_expect_tx(&s_wbar, S.wblk_bytes);
+            umma::bulk_g2s(sbase + S.wblk, wimg + (size_t)net * S.wblk_bytes, S.wblk_bytes, &s_wbar);
+        }
+    };
+    auto wait_weights = [&](const NetG& g, int out_dim) {
+        if (wimg == nullptr) { stage_weights(sm, sm0, S, params, g, d.obs_dim, out_dim); return; }
+        umma::mbar_wait(&s_wbar, wphase);
+        wphase ^= 1u;
+        if (g.ls >= 0 && tid < kMaxAct) {     // per-dimension constants of the diagonal Gaussian
+            float* gs = reinterpret_cast<float*>(sm + S.red) + 64;
+            const float sigma = expf(reinterpret_cast<const float*>(sm + S.ls)[tid]);
+            gs[tid] = 1.0f / (sigma * sigma);
+            gs[16 + tid] = logf(sigma) + 0.9189385332046727f;
+        }
+    };
     float* rowv = reinterpret_cast<float*>(sm + S.rowv);
     float* red = reinterpret_cast<float*>(sm + S.red);
     float* actt = reinterpret_cast<float*>(sm + S.act);
@@ -602,7 +681,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             // ================= critic ================================================================
             float h1[kCols], h2[kCols];
             tstamp(1);
-            stage_weights(sm, sm0, S, params, gc, d.obs_dim, 1);
+            if (!critic_issued) issue_weights(0);
+            critic_issued = false;
+            wait_weights(gc, 1);
             tstamp(2);
             trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
             tstamp(3);
@@ -621,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
                 if (lane == 0) red[warp] = sdv;                    // db3 (critic), one slot per warp
             }
             tstamp(4);
-            trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2, first);
+            trunk_backward(sm, sm0, S, tmem, pipe, gc, d.obs_dim, 1, grad, h1, h2, first, [&] { issue_weights(1); });
             tstamp(5);
             __syncthreads();
             if (tid == 0) out_acc(grad + gc.b3, (red[0] + red[1]) + (red[2] + red[3]), first);
@@ -630,7 +711,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             else if (m + 1 < n_mb && (int64_t)blockIdx.x < mb_tiles(m + 1)) { prefetch_rows(m + 1, blockIdx.x); next_rows_ready = true; }
 
             // ================= actor =================================================================
-            stage_weights(sm, sm0, S, params, ga, d.obs_dim, A);
+            wait_weights(ga, A);
             tstamp(6);
             trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
             tstamp(7);
@@ -671,7 +752,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
                 red[128 + 32 * warp + lane] = warp_transpose_sum32(cs);
             }
             tstamp(8);
-            trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2, first);
+            trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2, first, [] {});
             tstamp(9);
 
             // ================= loss sums + small gradients ===========================================
@@ -780,7 +861,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
             pv = pv - step_size * (mm / denom);         // addcdiv_(exp_avg, denom, -step_size)
             opt.exp_avg[i] = mm; opt.exp_avg_sq[i] = v; opt.params_w[i] = pv;
+            if (wimg != nullptr) img_scatter(d, S, sbase, i, pv, wimg);
         }
+        if (wimg != nullptr) umma::fence_proxy_async_all();      // image stores (generic proxy) before the peers' bulk copies
         if (tid == 0 && blockIdx.x == 0) {
             // the folded loss sums were written by the owner of the last slice before barrier 2
             const float* ex = opt.grad_scratch + d.n_params;
@@ -795,7 +878,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             }
         }
         tstamp(14);
-        if (m + 1 < n_mb) gbar.sync();                              // updated parameters visible to every CTA
+        if (m + 1 < n_mb) {
+            gbar.sync();                                            // updated parameters visible to every CTA
+            if (pre) { issue_weights(0); critic_issued = true; }
+        }
         tstamp(15);
     }
     umma::fence_before_sync();
@@ -965,7 +1051,7 @@ int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const
     const int64_t tiles = (hi - lo + kRows - 1) / kRows;
     const unsigned grid = (unsigned)imin(tiles, num_sms());
     ppo_tc_kernel<false><<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi - lo, hi, 1,
-                                                       global_rows, adv_moments, grad, AdamArgs{});
+                                                       global_rows, adv_moments, grad, AdamArgs{}, (uint8_t*)nullptr);
     return check_launch("ts_ppo_grad(tc)");
 }
 
@@ -975,7 +1061,7 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
                         const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
                         const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, const float* adv_moments,
                         float* partials, float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count,
-                        float* stats, cudaStream_t st) {
+                        float* stats, void* weight_image, cudaStream_t st) {
     const size_t smem = make_smem(d.obs_dim, 0).total;
     if (int e = configure_ppo_smem(smem)) return e;
     const int64_t last = end - (lo0 + (int64_t)(n_mb - 1) * mb_size);
@@ -989,10 +1075,19 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int64_t zero = 0;
+    uint8_t* wimg = static_cast<uint8_t*>(weight_image);
+    if (wimg) {   // (re)build the pre-split image from the current parameters: the host may have changed them
+        const Smem S = make_smem(d.obs_dim, 0);
+        TS_CUDA(cudaMemsetAsync(wimg, 0, 2 * (size_t)S.wblk_bytes, st));
+        weight_image_build_kernel<<<(unsigned)((d.n_params + 255) / 256), 256, 0, st>>>(params, d, wimg);
+        if (int e = check_launch("ts_ppo_update(weight image)")) return e;
+    }
     TS_CUDA(cudaLaunchKernelEx(&cfg, ppo_tc_kernel<true>, (const float*)params, d, hp, obs, act, adv, ret, logp_old, v_s, perm,
-                               lo0, mb_size, end, n_mb, zero, adv_moments, partials, opt));
+                               lo0, mb_size, end, n_mb, zero, adv_moments, partials, opt, wimg));
     return check_launch("ts_ppo_epoch(tc)");
 }
+
+int64_t weight_image_bytes(const ts_actor_critic_desc& d) { return tc_supported(d) ? 2 * (int64_t)make_smem(d.obs_dim, 0).wblk_bytes : 0; }
 
 int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
                       const float* in1, float* out1, int64_t n, cudaStream_t st) {

@@ -139,6 +139,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
         ::"r"(smem_u32(mbar)), "r"(parity) : "memory");
 }
 
+// transaction-count arrive + 1-D bulk copy global -> shared (TMA engine, completes on the mbarrier)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+// orders generic-proxy accesses (any state space) against later async-proxy accesses
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // ---- 3xTF32 split -----------------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
