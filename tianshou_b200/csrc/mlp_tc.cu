@@ -47,7 +47,7 @@ __device__ unsigned long long g_tc_timeline[32];
 __device__ int g_tc_timeline_on = 0;
 __device__ int g_tc_timeline_gate = 1;      // written and read by CTA 0 / thread 0 only: which step is recorded
 __device__ __forceinline__ void tstamp(int slot) {
-    if (g_tc_timeline_on && blockIdx.x == 0 && threadIdx.x == 0 && g_tc_timeline_gate) {
+    if (g_tc_timeline_on && (int)blockIdx.x == g_tc_timeline_on - 1 && threadIdx.x == 0 && g_tc_timeline_gate) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         g_tc_timeline[slot] = t;
@@ -538,17 +538,26 @@ struct AdamArgs {     // optimiser half of the fused single-GPU path
 
 struct GridBarrier {   // monotonic counter: the k-th use waits for k * gridDim.x arrivals
     unsigned int target;
-    __device__ __forceinline__ void sync() {
+    // Split phase.  arrive(): release at gpu scope (cumulative over the bar.sync) -- a release waits for the
+    // calling thread's OUTSTANDING LOADS too, so prefetches that should fly across the barrier are issued
+    // between arrive() and wait().
+    __device__ __forceinline__ void arrive() {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
-            __threadfence();
-            atomicAdd(&g_ep_arrive, 1u);
-            while (*((volatile unsigned int*)&g_ep_arrive) < target) {}
-            __threadfence();
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&g_ep_arrive) : "memory");
+        }
+    }
+    __device__ __forceinline__ void wait() {
+        if (threadIdx.x == 0) {
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&g_ep_arrive) : "memory");
+            } while (seen < target);
         }
         __syncthreads();
     }
+    __device__ __forceinline__ void sync() { arrive(); wait(); }
 };
 
 struct TileIn { float xv[8]; float av[kMaxAct]; float rv[4]; };   // one thread's share of a tile's gathers
@@ -573,6 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) uint64_t s_wbar;
+    __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
     __shared__ int32_t s_row[kRows];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = (int)gridDim.x;
@@ -659,14 +669,21 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         }
     };
 
+    double beta1_pow = 1.0, beta2_pow = 1.0;
+    if (EPOCH && tid == 256) { beta1_pow = pow(hp.beta1, (double)step0); beta2_pow = pow(hp.beta2, (double)step0); }
     bool staged = false;        // the tile's inputs were already stored by the previous step's prefetch
     tstamp(0);
     for (int m = 0; m < n_mb; ++m) {
         const int64_t lo = mb_lo(m), hi = mb_hi(m);
         const int64_t tiles = (hi - lo + kRows - 1) / kRows;
         const ppo::Scalars sc = ppo::make_scalars(hp, EPOCH ? hi - lo : global_rows, adv_moments ? adv_moments + 2 * m : nullptr);
-        if (blockIdx.x == 0 && tid == 0) g_tc_timeline_gate = (n_mb == 1 || m == n_mb - 2);   // a step WITH barrier 3
+        if (tid == 0 && g_tc_timeline_on && (int)blockIdx.x == g_tc_timeline_on - 1) g_tc_timeline_gate = (n_mb == 1 || m == n_mb - 2);   // a step WITH barrier 3
         tstamp(22);
+        if (EPOCH && tid == 256) {    // Adam bias corrections of this step, off the critical path
+            beta1_pow *= hp.beta1; beta2_pow *= hp.beta2;          // beta^(step0 + m + 1)
+            s_step_size = (float)(hp.lr / (1.0 - beta1_pow));
+            s_bc2_sqrt = (float)sqrt(1.0 - beta2_pow);
+        }
         bool next_rows_ready = false;   // s_row holds the rows of this CTA's first tile of minibatch m + 1
         for (int64_t t = blockIdx.x; t < tiles; t += P) {
             const bool first = (t == (int64_t)blockIdx.x);     // first tile of this CTA: gradients are stored, not added
@@ -781,7 +798,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         // ---- optimiser half of the step --------------------------------------------------------------
         __shared__ float s_part[4][128];
         __shared__ double s_red[4];
-        __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
         const int Pm = (int)tsb::imin((int64_t)P, tiles);           // partial rows written for this minibatch
         const int64_t slice = (width + P - 1) / P;
         const int64_t i0 = (int64_t)blockIdx.x * slice;
@@ -793,28 +809,33 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         // gathers of this CTA's tile of the next minibatch: in flight across the barrier
         TileIn pin;
         const bool pre = (m + 1 < n_mb) && (int64_t)blockIdx.x < mb_tiles(m + 1);
-        int nrows_next = 0;
+        if (pre && !next_rows_ready) prefetch_rows(m + 1, blockIdx.x);
+        gbar.arrive();
         if (pre) {
-            if (!next_rows_ready) { prefetch_rows(m + 1, blockIdx.x); __syncthreads(); }
-            nrows_next = (int)tsb::imin((int64_t)kRows, mb_hi(m + 1) - (mb_lo(m + 1) + (int64_t)blockIdx.x * kRows));
+            const int nrows_next = (int)tsb::imin((int64_t)kRows, mb_hi(m + 1) - (mb_lo(m + 1) + (int64_t)blockIdx.x * kRows));
             load_inputs(nrows_next, pin);
         }
-        gbar.sync();                                                // every partial row is complete
+        gbar.wait();                                                // every partial row is complete
         tstamp(11);
         if (pre) { store_inputs(pin); staged = true; }
+        // fold: thread (e, q) sums rows q, q + 4, ... of element i0 + e [+ 128, ...]; 32 loads in flight
         double ss = 0.0;
         for (int64_t c = i0; c < i1; c += 128) {
             const int64_t i = c + e;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
             if (i < i1) {
-                int p = q;
-                for (; p + 28 < Pm; p += 32) {
+                for (int p0 = q; p0 < Pm; p0 += 128) {
+                    float v[32];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) acc[u] += __ldcg(partials + (int64_t)(p + 4 * u) * width + i);
+                    for (int u = 0; u < 32; ++u) {
+                        const int p = p0 + 4 * u;
+                        v[u] = p < Pm ? __ldcg(partials + (int64_t)p * width + i) : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) { acc[0] += v[u]; acc[1] += v[u + 1]; acc[2] += v[u + 2]; acc[3] += v[u + 3]; }
                 }
-                for (; p < Pm; p += 4) acc[0] += __ldcg(partials + (int64_t)p * width + i);
             }
-            s_part[q][e] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+            s_part[q][e] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
             __syncthreads();
             if (q == 0 && i < i1) {
                 const float g = (s_part[0][e] + s_part[1][e]) + (s_part[2][e] + s_part[3][e]);
@@ -831,7 +852,14 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         __syncthreads();
         tstamp(12);
         if (tid == 0) atomicAdd(ss_cur, (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]));
-        gbar.sync();                                                // global sum of squares is complete
+        // the optimiser state of this thread's elements: loads in flight across the barrier
+        const bool one_pass = slice <= kThreads;      // (always, unless the network is far larger than the grid)
+        const int64_t i_own = i0 + tid;
+        const bool own = one_pass && i_own < i1 && i_own < d.n_params;
+        float pv_own = 0.f, m_own = 0.f, v_own = 0.f;
+        gbar.arrive();
+        if (own) { pv_own = opt.params_w[i_own]; m_own = opt.exp_avg[i_own]; v_own = opt.exp_avg_sq[i_own]; }
+        gbar.wait();                                                // global sum of squares is complete
         tstamp(13);
         if (tid == 0) {
             const float total_norm = (float)sqrt(*((volatile double*)ss_cur));
@@ -841,27 +869,27 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
                 coef = fminf(coef, 1.0f);
             }
             s_coef = coef; s_norm = total_norm;
-            const double bc1 = 1.0 - pow(hp.beta1, (double)step);
-            const double bc2 = 1.0 - pow(hp.beta2, (double)step);
-            s_step_size = (float)(hp.lr / bc1);
-            s_bc2_sqrt = (float)sqrt(bc2);
             if (blockIdx.x == 0) g_ep_ss[(m + 1) & 1] = 0.0;       // next step's accumulator (idle until barrier 3)
         }
         __syncthreads();
         const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
         const float w1 = (float)(1.0 - hp.beta1), w2 = (float)(1.0 - hp.beta2);
         const float beta2 = (float)hp.beta2, adam_eps = (float)hp.adam_eps, wd = (float)hp.weight_decay;
-        for (int64_t i = i0 + tid; i < i1 && i < d.n_params; i += kThreads) {
-            float g = opt.grad_scratch[i] * coef;
-            float pv = opt.params_w[i];
+        auto adam_elem = [&](int64_t i, float g, float pv, float mm, float v) {
+            g *= coef;
             if (wd != 0.0f) g = fmaf(wd, pv, g);
-            float mm = opt.exp_avg[i], v = opt.exp_avg_sq[i];
             mm = mm + w1 * (g - mm);                    // exp_avg.lerp_(grad, 1 - beta1)
             v = v * beta2 + w2 * g * g;                 // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
             const float denom = sqrtf(v) / bc2_sqrt + adam_eps;
             pv = pv - step_size * (mm / denom);         // addcdiv_(exp_avg, denom, -step_size)
             opt.exp_avg[i] = mm; opt.exp_avg_sq[i] = v; opt.params_w[i] = pv;
             if (wimg != nullptr) img_scatter(d, S, sbase, i, pv, wimg);
+        };
+        if (one_pass) {
+            if (own) adam_elem(i_own, opt.grad_scratch[i_own], pv_own, m_own, v_own);
+        } else {
+            for (int64_t i = i0 + tid; i < i1 && i < d.n_params; i += kThreads)
+                adam_elem(i, opt.grad_scratch[i], opt.params_w[i], opt.exp_avg[i], opt.exp_avg_sq[i]);
         }
         if (wimg != nullptr) umma::fence_proxy_async_all();      // image stores (generic proxy) before the peers' bulk copies
         if (tid == 0 && blockIdx.x == 0) {

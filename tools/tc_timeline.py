@@ -19,14 +19,15 @@ names = {0: "start", 1: "tile inputs staged", 2: "critic weights staged", 3: "cr
 with policy_within_training_step(algo.policy):
     algo.update(buffer=buf, batch_size=16384, repeat=1)
     torch.cuda.synchronize()
-    lib.ts_tc_timeline(1, None)
+    CTA = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    lib.ts_tc_timeline(1 + CTA, None)
     acc = {}
     n = 0
     for it in range(3):
         algo.update(buffer=buf, batch_size=16384, repeat=1)
         torch.cuda.synchronize()
         out = (C.c_uint64 * 32)()
-        lib.ts_tc_timeline(1, out)
+        lib.ts_tc_timeline(1 + CTA, out)
         t = np.array(out[:], dtype=np.int64)
         order = [0, 1, 2, 3, 4, 16, 17, 18, 19, 20, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
         # slots 16..20 are overwritten by the actor pass; report the actor's inner split separately
