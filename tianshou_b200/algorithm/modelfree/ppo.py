@@ -115,20 +115,9 @@ class PPO(ActorCriticOnPolicyAlgorithm):
         else:
             perms = None
 
-        adv_tmp = self._buf("adv_tmp", 32 + 8 * n_mb, torch.uint8)
-        adv_tmp.zero_()
-        bounds_c = (C.c_int64 * (2 * n_mb))(*[x for b in bounds for x in b])
 
         def run_repeats(perm_rows: torch.Tensor, r0: int, nrep: int, recompute: bool) -> None:
-            f = self._flat
-            call("ts_ppo_update", ptr(f.flat), ptr(f.grad), ptr(f.partials), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
-                 C.byref(self._desc), C.byref(hp), ptr(batch.obs), ptr(batch.obs_next), ptr(batch.act),
-                 ptr(batch.rew), ptr(batch.terminated), ptr(batch.truncated), ptr(batch.get("_unfinished")),
-                 ptr(batch.v_s), ptr(batch.returns), ptr(batch.adv), ptr(batch.logp_old),
-                 ptr(self._buf("v_next", N, torch.float32)), N, ptr(perm_rows), nrep, bounds_c, n_mb,
-                 int(recompute), float(self.gamma), float(self.gae_lambda),
-                 ptr(self._rms_device()) if self.return_scaling else None, float(self._eps),
-                 ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(f.weight_image), ptr(stats[r0 * n_mb:]), stream_ptr(dev))
+            self._device_passes(batch, perm_rows, bounds, hp, stats[r0 * n_mb:], nrep, recompute)
 
         if single_call:
             run_repeats(perms, 0, repeat, self.recompute_adv)
@@ -154,6 +143,24 @@ class PPO(ActorCriticOnPolicyAlgorithm):
         self._rms_end()
         self._flat.export_state(self.optim._optim)
         return result
+
+    def _device_passes(self, batch: Batch, perm_rows: torch.Tensor | None, bounds: list[tuple[int, int]], hp: Any,
+                       stats: torch.Tensor, nrep: int, recompute: bool) -> None:
+        """``nrep`` passes over the minibatches as ONE asynchronous C call (``ts_ppo_update``): per pass an
+        optional critic + GAE recompute and one persistent launch covering every optimiser step."""
+        f, dev = self._flat, self.device
+        N, n_mb = batch.obs.shape[0], len(bounds)
+        adv_tmp = self._buf("adv_tmp", 32 + 8 * n_mb, torch.uint8)
+        adv_tmp.zero_()
+        bounds_c = (C.c_int64 * (2 * n_mb))(*[x for b in bounds for x in b])
+        call("ts_ppo_update", ptr(f.flat), ptr(f.grad), ptr(f.partials), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
+             C.byref(self._desc), C.byref(hp), ptr(batch.obs), ptr(batch.obs_next), ptr(batch.act),
+             ptr(batch.rew), ptr(batch.terminated), ptr(batch.truncated), ptr(batch.get("_unfinished")),
+             ptr(batch.v_s), ptr(batch.returns), ptr(batch.adv), ptr(batch.logp_old),
+             ptr(self._buf("v_next", N, torch.float32)), N, ptr(perm_rows), nrep, bounds_c, n_mb,
+             int(recompute), float(self.gamma), float(self.gae_lambda),
+             ptr(self._rms_device()) if self.return_scaling else None, float(self._eps),
+             ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(f.weight_image), ptr(stats), stream_ptr(dev))
 
     def _distributed_repeat(self, batch: Batch, perm: torch.Tensor, bounds: list[tuple[int, int]], hp: Any,
                             stats: torch.Tensor, rank: int, wsize: int) -> None:
