@@ -927,9 +927,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
 
 
 // ---- forward-only kernels (value pass / log-prob pass), persistent over 128-row tiles -----------
+// Two tiles are in flight per CTA (slots 0 / 1: own X, H1 operands and D1, D2 accumulators): the MMAs of one
+// slot run on the tensor core while the 16 warps do the other slot's epilogues, and the next tiles' rows are
+// loaded from global memory one stage ahead of their conversion into operands.
 struct SmemF {
     int KXP;
-    Mat X, H1, W1, W2;
+    Mat X[2], H1[2], W1, W2;
     uint32_t w3f, b1, b2, b3, ls, part;
     uint32_t total;
 };
@@ -940,8 +943,10 @@ __host__ __device__ inline SmemF make_smem_f(int obs_dim, uint32_t sbase) {
     auto mat = [&](Mat& m, int rows, int cols) {
         m.base = sbase + o; m.part = mat_bytes(rows, cols); m.RS = (uint32_t)(cols / 8) * 128u; o += 3u * m.part;
     };
-    mat(s.X, kRows, s.KXP);
-    mat(s.H1, kRows, H);
+    mat(s.X[0], kRows, s.KXP);
+    mat(s.X[1], kRows, s.KXP);
+    mat(s.H1[0], kRows, H);
+    mat(s.H1[1], kRows, H);
     mat(s.W1, H, s.KXP);
     mat(s.W2, H, H);
     s.w3f = o;  o += kMaxAct * H * 4;
@@ -954,6 +959,26 @@ __host__ __device__ inline SmemF make_smem_f(int obs_dim, uint32_t sbase) {
     return s;
 }
 
+// all threads: publish smem operands / retire TMEM reads, then warp 0 issues `f` and commits to `bar` (no wait)
+template <class F>
+__device__ __forceinline__ void mma_issue(uint64_t* bar, F&& f) {
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    const int warp_u = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    if (warp_u == 0) {
+        umma::fence_after_sync();
+        f();
+        if (umma::elect_one()) umma::mma_commit(bar);
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t& phase) {
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+}
+
 // MODE 0: out0[r] = critic(in0[r]) and (if in1) out1[r] = critic(in1[r])      (a2c.py:123-126)
 // MODE 1: out0[r] = log N(in1[r] | mu(in0[r]), exp(logstd)), out1 = mu (nullable)   (ppo.py:157-161)
 template <int MODE>
@@ -962,7 +987,7 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
     float* __restrict__ out0, const float* __restrict__ in1, float* __restrict__ out1, int64_t n) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[2][2];      // [slot][layer]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = umma::smem_u32(sm);
     uint8_t* sm0 = sm - sbase;
@@ -970,8 +995,12 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
     const int out_dim = MODE == 0 ? 1 : d.act_dim;
     const NetG g = MODE == 0 ? NetG{d.c_w1, d.c_b1, d.c_w2, d.c_b2, d.c_w3, d.c_b3, -1}
                              : NetG{d.a_w1, d.a_b1, d.a_w2, d.a_b2, d.a_w3, d.a_b3, d.a_logstd};
-    if (warp == 0) umma::tmem_alloc(&s_tmem, 128);
-    if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 256);
+    if (tid == 0) {
+        umma::mbar_init(&s_bar[0][0], 1); umma::mbar_init(&s_bar[0][1], 1);
+        umma::mbar_init(&s_bar[1][0], 1); umma::mbar_init(&s_bar[1][1], 1);
+        umma::fence_mbar_init();
+    }
     // weights: W1, W2 as tensor-core operands; head weights / biases as fp32
     stage_chunks(sm0, S.W1, H, d.obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * d.obs_dim; });
     stage_chunks(sm0, S.W2, H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; });
@@ -985,35 +1014,48 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
     for (int e = tid; e < H; e += kThreads) { b1[e] = __ldg(params + g.b1 + e); b2[e] = __ldg(params + g.b2 + e); }
     if (tid < kMaxAct) {
         b3[tid] = tid < out_dim ? __ldg(params + g.b3 + tid) : 0.0f;
-        ls[tid] = (MODE == 1 && tid < out_dim) ? __ldg(params + g.ls + tid) : 0.0f;
+        // sigma_a = exp(logstd_a), once per CTA; the log-prob keeps torch's expression order (normal_logp_term)
+        ls[tid] = (MODE == 1 && tid < out_dim) ? expf(__ldg(params + g.ls + tid)) : 1.0f;
     }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    Pipe pipe{&s_bar, 0u};
+    uint32_t ph[2][2] = {{0u, 0u}, {0u, 0u}};
 
     const int64_t tiles_per = (n + kRows - 1) / kRows;
     const int64_t tiles = tiles_per * ((MODE == 0 && in1) ? 2 : 1);
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const bool second = t >= tiles_per;
-        const int64_t row0 = (second ? t - tiles_per : t) * kRows;
-        const int nrows = (int)tsb::imin((int64_t)kRows, n - row0);
-        const float* src = (MODE == 0 && second) ? in1 : in0;
-        // the tile's rows are contiguous in memory: coalesced read, scattered bf16x3 store
-        stage_chunks(sm0, S.X, kRows, d.obs_dim, S.KXP, [&](int r) {
-            return r < nrows ? src + (row0 + r) * d.obs_dim : (const float*)nullptr;
-        });
-        pipe.run([&] { gemm_kx(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
+    const int64_t my_n = tiles > (int64_t)blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
+    auto tile_of = [&](int64_t k) { return (int64_t)blockIdx.x + k * gridDim.x; };
+    auto tile_src = [&](int64_t t, const float*& src, int64_t& row0, int& nrows, bool& second) {
+        second = t >= tiles_per;
+        row0 = (second ? t - tiles_per : t) * kRows;
+        nrows = (int)tsb::imin((int64_t)kRows, n - row0);
+        src = (MODE == 0 && second) ? in1 : in0;
+    };
+    // the tile's rows are contiguous in memory: coalesced read (x_load), bf16x3 conversion later (x_store)
+    auto x_load = [&](int64_t k, float (&xv)[8]) {
+        const float* src; int64_t row0; int nrows; bool second;
+        tile_src(tile_of(k), src, row0, nrows, second);
+        chunk_load(kRows, d.obs_dim, S.KXP, [&](int r) { return r < nrows ? src + (row0 + r) * d.obs_dim : (const float*)nullptr; }, xv);
+    };
+    auto l1 = [&](int slot) {
+        mma_issue(&s_bar[slot][0], [&] { gemm_kx(tmem + 128u * slot + cD1, 128, H, S.X[slot], 0, S.W1, 0, S.KXP); });
+    };
+    auto epi1_l2 = [&](int slot) {     // h1 = tanh(D1 + b1) -> H1[slot]; issue layer 2
+        mma_wait(&s_bar[slot][0], ph[slot][0]);
+        float h1[kCols];
+        epi_tanh(sm0, S.H1[slot], tmem + 128u * slot, cD1, b1, h1);
+        mma_issue(&s_bar[slot][1], [&] { gemm<H / 16>(tmem + 128u * slot + cD2, 128, H, S.H1[slot], 0, S.W2, 0); });
+    };
+    auto epi2 = [&](int slot, int64_t k) {   // h2 = tanh(D2 + b2) in registers; head = h2 . W3^T (K = 64 split over the four column groups)
+        const float* src; int64_t row0; int nrows; bool second;
+        tile_src(tile_of(k), src, row0, nrows, second);
+        mma_wait(&s_bar[slot][1], ph[slot][1]);
         {
-            float h1[kCols];
-            epi_tanh(sm0, S.H1, tmem, cD1, b1, h1);
-        }
-        pipe.run([&] { gemm<H / 16>(tmem + cD2, 128, H, S.H1, 0, S.W2, 0); });
-        {   // h2 = tanh(D2 + b2) stays in registers; head = h2 . W3^T (K = 64 split over the four column groups)
             const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
             float v[kCols];
-            umma::tmem_ld16(tmem + ((32u * (warp & 3)) << 16) + cD2 + c0, v);
+            umma::tmem_ld16(tmem + 128u * slot + ((32u * (warp & 3)) << 16) + cD2 + c0, v);
 #pragma unroll
             for (int j = 0; j < kCols; ++j) v[j] = tanh_mufu(v[j] + b2[c0 + j]);
             for (int a = 0; a < out_dim; ++a) {
@@ -1034,16 +1076,32 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
                 for (int a = 0; a < out_dim; ++a) {
                     const float mu = (part[r * kMaxAct + a] + part[(kRows + r) * kMaxAct + a]) +
                                      (part[(2 * kRows + r) * kMaxAct + a] + part[(3 * kRows + r) * kMaxAct + a]) + b3[a];
-                    lp += ppo::normal_logp_term(__ldg(in1 + (row0 + r) * out_dim + a), mu, expf(ls[a]));
+                    lp += ppo::normal_logp_term(__ldg(in1 + (row0 + r) * out_dim + a), mu, ls[a]);
                     if (out1) out1[(row0 + r) * out_dim + a] = mu;
                 }
                 out0[row0 + r] = lp;
             }
         }
+        __syncthreads();     // `part` is free again
+    };
+
+    float xa[8], xb[8];
+    if (my_n > 0) { x_load(0, xa); chunk_store(sm0, S.X[0], kRows, S.KXP, xa); l1(0); }
+    if (my_n > 1) { x_load(1, xb); chunk_store(sm0, S.X[1], kRows, S.KXP, xb); l1(1); }
+    for (int64_t k = 0; k < my_n; k += 2) {
+        const bool hasB = k + 1 < my_n, nextA = k + 2 < my_n, nextB = k + 3 < my_n;
+        if (nextA) x_load(k + 2, xa);              // global loads fly under the epilogues below
+        epi1_l2(0);
+        if (nextB) x_load(k + 3, xb);
+        if (hasB) epi1_l2(1);                      // layer 2 of slot 0 runs on the tensor core meanwhile
+        if (nextA) { chunk_store(sm0, S.X[0], kRows, S.KXP, xa); l1(0); }     // X[0] / D1[0] are free: layer 1 of tile k was consumed
+        epi2(0, k);
+        if (nextB) { chunk_store(sm0, S.X[1], kRows, S.KXP, xb); l1(1); }
+        if (hasB) epi2(1, k + 1);
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 128);
+    if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace
