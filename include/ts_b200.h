@@ -278,6 +278,51 @@ int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, f
                   double gamma, double lam, double* rms_state, double rms_eps, void* gae_ws,
                   void* adv_tmp, void* weight_image, float* stats, ts_stream_t stream);
 
+/* ---- multi-GPU fused update: gradient all-reduce INSIDE the epoch kernel over NVLink peer memory -------------
+ * Replaces, for one process per GPU (data-parallel replicas, each rank owns its own rollout shard), the
+ * reference's single-process optimiser step (ppo.py:215-218) x world ranks: the loss is the mean over the
+ * union of the ranks' local minibatches, the summed gradient / global-norm clip / Adam step are bit-identical
+ * on every rank.  No NCCL call on the data path: after the local fold every CTA pushes its slice of the
+ * gradient as (fp32 value, sequence number) 8-byte packets straight into every peer's exchange buffer and
+ * gathers the peers' packets from its own.
+ *
+ * Plumbing: ts_peer_alloc cudaMalloc's + zeroes a buffer and returns its CUDA IPC handle (TS_PEER_HANDLE_BYTES
+ * opaque bytes the host exchanges, e.g. with torch.distributed.all_gather); ts_peer_open maps a peer's buffer
+ * into this process; ts_peer_close / ts_peer_free undo them.  Buffer size: ts_ppo_peer_buffer_bytes(desc, world)
+ * (world <= 8).  The buffers carry a sequence number across launches: allocate once, zero-initialised, and use
+ * them for every update of the same replicas. */
+#define TS_PEER_HANDLE_BYTES 64
+int ts_peer_alloc(int64_t bytes, void** ptr_out, uint8_t* handle_out /* TS_PEER_HANDLE_BYTES */);
+int ts_peer_open(const uint8_t* handle, void** ptr_out);
+int ts_peer_close(void* ptr);
+int ts_peer_free(void* ptr);
+int64_t ts_ppo_peer_buffer_bytes(const ts_actor_critic_desc* desc, int32_t world);
+
+/* Per-minibatch advantage moments of one pass across ranks (ppo.py:181-183 on the global minibatch):
+ * ts_epoch_adv_sums writes (sum, sum of squares) in f64 per minibatch of THIS rank's shard; the host all-reduces
+ * the 2 * n_minibatch doubles; ts_epoch_adv_finalize turns them into (mean, unbiased std) float pairs for
+ * minibatches of world * (hi - lo) rows. */
+int ts_epoch_adv_sums(const float* adv, const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end,
+                      int32_t n_minibatch, double* sums, ts_stream_t stream);
+int ts_epoch_adv_finalize(const double* sums, int64_t lo0, int64_t mb_size, int64_t end, int32_t n_minibatch,
+                          int32_t world, float* out, ts_stream_t stream);
+
+/* ONE pass over the minibatches [lo0 + m * mb_size, ...) (last one ends at `end`; Batch.split bounds,
+ * batch.py:1199-1215) of this rank's shard, every optimiser step of the pass in one persistent launch, gradients
+ * summed over the `world` ranks in-kernel.  Arguments as ts_ppo_update (perm: this pass's N int32 or NULL;
+ * stats: n_minibatch rows, global losses).  adv_moments: n_minibatch (mean, std) pairs from
+ * ts_epoch_adv_finalize, required iff hp->advantage_normalization.  peer_buffers: host array of `world` device
+ * pointers (index = rank; own buffer from ts_peer_alloc, the others from ts_peer_open); world == 1: may be NULL.
+ * Every rank must call with the same shapes and the same number of minibatches.  A peer that does not show
+ * up within 20 s traps the kernel (CUDA error at the next synchronisation) instead of hanging the GPU. */
+int ts_ppo_epoch_multi(float* params, float* grad, float* partials, float* exp_avg, float* exp_avg_sq,
+                       int64_t* step_count, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
+                       const float* obs, const float* act, const float* adv, const float* returns,
+                       const float* logp_old, const float* v_s, const int32_t* perm, int64_t lo0,
+                       int64_t mb_size, int64_t end, int32_t n_minibatch, const float* adv_moments,
+                       void* weight_image, float* stats, int32_t rank, int32_t world,
+                       void* const* peer_buffers /* host */, ts_stream_t stream);
+
 /* Device-side minibatch order (opt-in alternative to np.random.permutation, batch.py:1209):
  * out[r*n + i] = pi_r(i), pi_r a keyed bijection of [0,n) (cycle-walking Feistel/Philox). */
 int ts_make_permutation(uint64_t seed, int32_t first_epoch, int32_t n_epochs, int64_t n,

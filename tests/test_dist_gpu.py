@@ -1,5 +1,7 @@
-"""Multi-GPU path (one process per GPU, NCCL): with identical rollouts on both ranks the averaged
-gradient equals the single-GPU gradient, so the update must reproduce the reference run."""
+"""Multi-GPU path (one process per GPU): with identical rollouts on both ranks the averaged gradient
+equals the single-GPU gradient, so the update must reproduce the reference run -- both through the fused
+kernel (gradient sum inside the persistent epoch kernel over NVLink peer memory, ``path="p2p"``) and
+through the per-step NCCL all-reduce (``path="nccl"``)."""
 import os
 import socket
 
@@ -18,14 +20,15 @@ def _free_port() -> int:
     return p
 
 
-def _worker(rank: int, world_size: int, port: int, variant: str, out_dir: str) -> None:
+def _worker(rank: int, world_size: int, port: int, variant: str, path: str, out_dir: str) -> None:
     import torch.distributed as dist
 
     from test_ppo_gpu import ppo_kwargs
     from tianshou_b200.utils import policy_within_training_step
     from ts_testutil import PARAM_ORDER, build_ppo, load_golden, named_params, restore_vector_buffer
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size),
+                      TS_B200_NO_P2P="1" if path == "nccl" else "0")
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=dev)
@@ -41,6 +44,8 @@ def _worker(rank: int, world_size: int, port: int, variant: str, out_dir: str) -
             with policy_within_training_step(algo.policy):
                 stats = algo.update(buffer=buf, batch_size=None if bs < 0 else bs, repeat=int(g["cfg_repeat"]))
             assert stats.gradient_steps == int(g[f"u{u}_gradient_steps"])
+            # the path under test is the one that ran (no silent fallback)
+            assert (algo._scratch.get("peer_exchange") is not None) == (path == "p2p"), "wrong multi-GPU path"
             ref_losses = g[f"u{u}_losses"]
             np.testing.assert_allclose(stats.loss.mean, ref_losses[:, 0].mean(), rtol=5e-4, atol=2e-5)
             np.testing.assert_allclose(stats.vf_loss.mean, ref_losses[:, 2].mean(), rtol=5e-4, atol=2e-5)
@@ -54,11 +59,12 @@ def _worker(rank: int, world_size: int, port: int, variant: str, out_dir: str) -
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("path", ["p2p", "nccl"])
 @pytest.mark.parametrize("variant", ["A", "B"])
-def test_two_rank_update_matches_reference(variant, tmp_path):
+def test_two_rank_update_matches_reference(variant, path, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), variant, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), variant, path, str(tmp_path)), nprocs=2, join=True)
     a, b = torch.load(tmp_path / "flat0.pt"), torch.load(tmp_path / "flat1.pt")
     assert torch.equal(a, b), "replicas diverged"      # same all-reduced gradient, same Adam step: bit-identical

@@ -82,13 +82,23 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_ppo_update": [_P, _P, _P, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams),
                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32,
                       C.POINTER(_I64), _I32, _I32, _D, _D, _P, _D, _P, _P, _P, _P, _P],
+    "ts_peer_alloc": [_I64, C.POINTER(C.c_void_p), _P],
+    "ts_peer_open": [_P, C.POINTER(C.c_void_p)],
+    "ts_peer_close": [_P],
+    "ts_peer_free": [_P],
+    "ts_epoch_adv_sums": [_P, _P, _I64, _I64, _I64, _I32, _P, _P],
+    "ts_epoch_adv_finalize": [_P, _I64, _I64, _I64, _I32, _I32, _P, _P],
+    "ts_ppo_epoch_multi": [_P, _P, _P, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams),
+                           _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32,
+                           C.POINTER(C.c_void_p), _P],
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
     "ts_narrow_i64_i32": [_P, _I64, _P, _P],
     "ts_tc_timeline": [_I32, _P],
     "ts_umma_selftest": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 OTHER_SYMBOLS = ["ts_version", "ts_last_error", "ts_launch_count", "ts_reset_launch_count",
-                 "ts_gae_workspace_bytes", "ts_ppo_partial_rows", "ts_ppo_weight_image_bytes"]
+                 "ts_gae_workspace_bytes", "ts_ppo_partial_rows", "ts_ppo_weight_image_bytes",
+                 "ts_ppo_peer_buffer_bytes"]
 
 _lib: C.CDLL | None = None
 
@@ -118,6 +128,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ts_ppo_partial_rows.restype = C.c_int32
     lib.ts_ppo_weight_image_bytes.argtypes = [C.POINTER(ActorCriticDesc)]
     lib.ts_ppo_weight_image_bytes.restype = C.c_int64
+    lib.ts_ppo_peer_buffer_bytes.argtypes = [C.POINTER(ActorCriticDesc), _I32]
+    lib.ts_ppo_peer_buffer_bytes.restype = C.c_int64
     if path is None:
         _lib = lib
     return lib

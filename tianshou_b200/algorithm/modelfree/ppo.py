@@ -137,6 +137,8 @@ class PPO(ActorCriticOnPolicyAlgorithm):
                     perm_r = perms[r]
                 if wsize == 1:
                     run_repeats(perm_r, r, 1, False)
+                elif self._peer_exchange(bounds) is not None:
+                    self._fused_distributed_pass(batch, perm_r, bounds, hp, stats[r * n_mb:], rank, wsize)
                 else:
                     self._distributed_repeat(batch, perm_r, bounds, hp, stats[r * n_mb:], rank, wsize)
         result = self._stats_from_device(stats)   # the only host sync of the update
@@ -161,6 +163,46 @@ class PPO(ActorCriticOnPolicyAlgorithm):
              int(recompute), float(self.gamma), float(self.gae_lambda),
              ptr(self._rms_device()) if self.return_scaling else None, float(self._eps),
              ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(f.weight_image), ptr(stats), stream_ptr(dev))
+
+    # ------------------------------------------------------------------ multi-GPU, fused (NVLink peer memory)
+    def _peer_exchange(self, bounds: list[tuple[int, int]]):
+        """The exchange buffers of the in-kernel all-reduce, created collectively on first use.  None ->
+        NCCL path (``TS_B200_NO_P2P=1``, irregular minibatch bounds, a network the tensor-core kernels do
+        not cover, or peer mapping unavailable)."""
+        import os
+
+        from ...parallel import PeerExchange
+        if "peer_exchange" not in self._scratch:
+            size = bounds[0][1] - bounds[0][0]
+            regular = all(lo == bounds[0][0] + m * size and (m == len(bounds) - 1 or hi == lo + size)
+                          for m, (lo, hi) in enumerate(bounds))
+            usable = (os.environ.get("TS_B200_NO_P2P", "0") != "1" and regular
+                      and self._flat.weight_image is not None and os.environ.get("TS_B200_FORCE_SIMT", "0") != "1")
+            # the decision must be identical on every rank: all inputs above are (shapes, env) -- replicas agree
+            self._scratch["peer_exchange"] = PeerExchange.create(self._desc, self.device) if usable else None
+        return self._scratch["peer_exchange"]
+
+    def _fused_distributed_pass(self, batch: Batch, perm: torch.Tensor | None, bounds: list[tuple[int, int]], hp: Any,
+                                stats: torch.Tensor, rank: int, wsize: int) -> None:
+        """One pass over the minibatches of this rank's shard as ONE persistent launch; the gradient sum over
+        the ranks happens inside the kernel (8-byte packets over NVLink, ``ts_ppo_epoch_multi``).  The only
+        collective on the host side is the all-reduce of the per-minibatch advantage sums when
+        ``advantage_normalization`` is on (2 * n_minibatch doubles per pass)."""
+        f, st = self._flat, stream_ptr(self.device)
+        ex = self._scratch["peer_exchange"]
+        n_mb = len(bounds)
+        lo0, size, end = bounds[0][0], bounds[0][1] - bounds[0][0], bounds[-1][1]
+        adv_mom = None
+        if self.advantage_normalization:
+            sums = self._buf("epoch_adv_sums", 2 * n_mb, torch.float64)
+            call("ts_epoch_adv_sums", ptr(batch.adv), ptr(perm), lo0, size, end, n_mb, ptr(sums), st)
+            allreduce_sum_(sums)
+            adv_mom = self._buf("epoch_adv_mom", 2 * n_mb, torch.float32)
+            call("ts_epoch_adv_finalize", ptr(sums), lo0, size, end, n_mb, wsize, ptr(adv_mom), st)
+        call("ts_ppo_epoch_multi", ptr(f.flat), ptr(f.grad), ptr(f.partials), ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
+             C.byref(self._desc), C.byref(hp), ptr(batch.obs), ptr(batch.act), ptr(batch.adv), ptr(batch.returns),
+             ptr(batch.logp_old), ptr(batch.v_s), ptr(perm), lo0, size, end, n_mb, ptr(adv_mom), ptr(f.weight_image),
+             ptr(stats), rank, wsize, ex.ptrs, st)
 
     def _distributed_repeat(self, batch: Batch, perm: torch.Tensor, bounds: list[tuple[int, int]], hp: Any,
                             stats: torch.Tensor, rank: int, wsize: int) -> None:

@@ -11,6 +11,19 @@ namespace tsb {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Peer exchange of the multi-GPU fused update (one process per GPU, buffers shared through CUDA IPC).
+// Every rank owns one exchange buffer:  [256-byte header: uint32 seq][world][2][width] 8-byte packets.
+// A packet is (fp32 value, uint32 sequence number) written with ONE 8-byte store by the producing rank
+// directly into the consumer's buffer over NVLink; the consumer polls the sequence half (no fences, no
+// separate flags: the NCCL "LL" idea).  Slot parity = seq & 1.
+constexpr int kMaxPeers = 8;
+struct PeerArgs {
+    int rank = 0, world = 1;
+    unsigned long long* recv[kMaxPeers] = {};   // packet areas of every rank's buffer (device pointers valid on THIS device)
+    unsigned int* hdr = nullptr;                // this rank's header (sequence number of the last completed step)
+};
+constexpr size_t kPeerHeaderBytes = 256;
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -708,6 +708,40 @@ __global__ void __launch_bounds__(1024) epoch_adv_moments_kernel(const float* __
     }
 }
 
+// multi-GPU variant: per-minibatch (sum, sum of squares) in f64 -> all-reduce on the host side -> finalize
+__global__ void __launch_bounds__(1024) epoch_adv_sums_kernel(const float* __restrict__ adv, const int32_t* __restrict__ perm,
+                                                              int64_t lo0, int64_t mb_size, int64_t end, int n_mb,
+                                                              double* __restrict__ sums) {
+    __shared__ double s1[32], s2[32];
+    const int m = blockIdx.x;
+    const int64_t lo = lo0 + (int64_t)m * mb_size, hi = m == n_mb - 1 ? end : lo + mb_size;
+    double a = 0.0, b = 0.0;
+    for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+        const double v = adv[perm ? (int64_t)perm[p] : p];
+        a += v; b += v * v;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { a += tsb::shfl_xor_f64(a, off); b += tsb::shfl_xor_f64(b, off); }
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { x += s1[w]; y += s2[w]; }
+        sums[2 * m] = x; sums[2 * m + 1] = y;
+    }
+}
+__global__ void epoch_adv_finalize_kernel(const double* __restrict__ sums, int64_t lo0, int64_t mb_size, int64_t end, int n_mb,
+                                          int world, float* __restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mb) return;
+    const int64_t lo = lo0 + (int64_t)m * mb_size, hi = m == n_mb - 1 ? end : lo + mb_size;
+    const int64_t n = (hi - lo) * world;
+    const double mean = sums[2 * m] / (double)n;
+    double var = (sums[2 * m + 1] - sums[2 * m] * mean) / (double)(n > 1 ? n - 1 : 1);
+    if (var < 0.0) var = 0.0;
+    out[2 * m] = (float)mean; out[2 * m + 1] = (float)sqrt(var);
+}
+
 // ---- keyed bijection of [0, n): balanced Feistel on an even number of bits + cycle walking ----
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
@@ -777,7 +811,7 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
                         const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
                         const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, const float* adv_moments,
                         float* partials, float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count,
-                        float* stats, void* weight_image, cudaStream_t st);
+                        float* stats, void* weight_image, const PeerArgs& px, cudaStream_t st);
 int64_t weight_image_bytes(const ts_actor_critic_desc& d);
 static bool simt_forced() {
     static const bool f = [] { const char* e = getenv("TS_B200_FORCE_SIMT"); return e && e[0] == '1'; }();
@@ -941,7 +975,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
             }
             if (int e = tsb::launch_ppo_epoch_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo0, mb_size, end,
                                                  n_minibatch, hp->advantage_normalization ? epoch_mom : nullptr, partials, grad,
-                                                 exp_avg, exp_avg_sq, step_count, rows, weight_image, tsb::as_stream(stream))) return e;
+                                                 exp_avg, exp_avg_sq, step_count, rows, weight_image, tsb::PeerArgs{}, tsb::as_stream(stream))) return e;
             continue;
         }
         for (int m = 0; m < n_minibatch; ++m) {
@@ -954,7 +988,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
             if (fused) {   // irregular bounds: one launch per optimiser step
                 if (int e = tsb::launch_ppo_epoch_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, pr, lo, hi - lo, hi,
                                                      1, adv_mom, partials, grad, exp_avg, exp_avg_sq, step_count, row,
-                                                     weight_image, tsb::as_stream(stream))) return e;
+                                                     weight_image, tsb::PeerArgs{}, tsb::as_stream(stream))) return e;
                 continue;
             }
             int32_t n_part = 0;
@@ -964,4 +998,46 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
         }
     }
     return 0;
+}
+
+extern "C" int ts_epoch_adv_sums(const float* adv, const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end,
+                                 int32_t n_minibatch, double* sums, ts_stream_t stream) {
+    TS_REQUIRE(adv && sums && n_minibatch > 0 && mb_size > 0, "ts_epoch_adv_sums: bad arguments");
+    epoch_adv_sums_kernel<<<n_minibatch, 1024, 0, tsb::as_stream(stream)>>>(adv, perm, lo0, mb_size, end, n_minibatch, sums);
+    return tsb::check_launch("ts_epoch_adv_sums");
+}
+
+extern "C" int ts_epoch_adv_finalize(const double* sums, int64_t lo0, int64_t mb_size, int64_t end, int32_t n_minibatch,
+                                     int32_t world, float* out, ts_stream_t stream) {
+    TS_REQUIRE(sums && out && n_minibatch > 0 && world >= 1, "ts_epoch_adv_finalize: bad arguments");
+    epoch_adv_finalize_kernel<<<(n_minibatch + 127) / 128, 128, 0, tsb::as_stream(stream)>>>(sums, lo0, mb_size, end, n_minibatch, world, out);
+    return tsb::check_launch("ts_epoch_adv_finalize");
+}
+
+extern "C" int ts_ppo_epoch_multi(float* params, float* grad, float* partials, float* exp_avg, float* exp_avg_sq,
+                                  int64_t* step_count, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
+                                  const float* obs, const float* act, const float* adv, const float* returns,
+                                  const float* logp_old, const float* v_s, const int32_t* perm, int64_t lo0,
+                                  int64_t mb_size, int64_t end, int32_t n_minibatch, const float* adv_moments,
+                                  void* weight_image, float* stats, int32_t rank, int32_t world,
+                                  void* const* peer_buffers, ts_stream_t stream) {
+    if (check_desc(desc, "ts_ppo_epoch_multi")) return 2;
+    TS_REQUIRE(hp && params && grad && partials && stats && n_minibatch > 0 && mb_size > 0 && end > lo0 + (int64_t)(n_minibatch - 1) * mb_size,
+               "ts_ppo_epoch_multi: bad arguments");
+    TS_REQUIRE(tsb::tc_supported(*desc) && !tsb::simt_forced(), "ts_ppo_epoch_multi: network shape not covered by the tensor-core kernels");
+    TS_REQUIRE(world >= 1 && world <= tsb::kMaxPeers && rank >= 0 && rank < world, "ts_ppo_epoch_multi: bad rank / world");
+    TS_REQUIRE(!hp->advantage_normalization || adv_moments, "ts_ppo_epoch_multi: advantage normalisation needs the global per-minibatch moments");
+    tsb::PeerArgs px;
+    px.rank = rank; px.world = world;
+    if (world > 1) {
+        TS_REQUIRE(peer_buffers, "ts_ppo_epoch_multi: peer_buffers required for world > 1");
+        for (int r = 0; r < world; ++r) {
+            TS_REQUIRE(peer_buffers[r], "ts_ppo_epoch_multi: null peer buffer");
+            px.recv[r] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(peer_buffers[r]) + tsb::kPeerHeaderBytes);
+        }
+        px.hdr = static_cast<unsigned int*>(peer_buffers[rank]);
+    }
+    return tsb::launch_ppo_epoch_tc(params, *desc, *hp, obs, act, adv, returns, logp_old, v_s, perm, lo0, mb_size, end, n_minibatch,
+                                    adv_moments, partials, grad, exp_avg, exp_avg_sq, step_count, stats, weight_image, px,
+                                    tsb::as_stream(stream));
 }

@@ -577,7 +577,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     const float* __restrict__ obs, const float* __restrict__ act, const float* __restrict__ adv,
     const float* __restrict__ ret, const float* __restrict__ logp_old, const float* __restrict__ v_s,
     const int32_t* __restrict__ perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, int64_t global_rows,
-    const float* __restrict__ adv_moments, float* __restrict__ partials, const AdamArgs opt, uint8_t* wimg /* nullable */) {
+    const float* __restrict__ adv_moments, float* __restrict__ partials, const AdamArgs opt, uint8_t* wimg /* nullable */,
+    const tsb::PeerArgs px) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_bar;
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     const NetG ga{d.a_w1, d.a_b1, d.a_w2, d.a_b2, d.a_w3, d.a_b3, d.a_logstd};
     const NetG gc{d.c_w1, d.c_b1, d.c_w2, d.c_b2, d.c_w3, d.c_b3, -1};
     const int64_t step0 = EPOCH ? *opt.step_count : 0;
+    const unsigned int seq0 = (EPOCH && px.world > 1) ? *((volatile unsigned int*)px.hdr) : 0u;
 
     if (warp == 0) umma::tmem_alloc(&s_tmem, kTmemCols);
     if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::mbar_init(&s_wbar, 1); umma::fence_mbar_init(); }
@@ -676,7 +678,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     for (int m = 0; m < n_mb; ++m) {
         const int64_t lo = mb_lo(m), hi = mb_hi(m);
         const int64_t tiles = (hi - lo + kRows - 1) / kRows;
-        const ppo::Scalars sc = ppo::make_scalars(hp, EPOCH ? hi - lo : global_rows, adv_moments ? adv_moments + 2 * m : nullptr);
+        // the loss is the mean over the GLOBAL minibatch: every rank contributes hi - lo rows of its own shard
+        const ppo::Scalars sc = ppo::make_scalars(hp, EPOCH ? (hi - lo) * px.world : global_rows, adv_moments ? adv_moments + 2 * m : nullptr);
         if (tid == 0 && g_tc_timeline_on && (int)blockIdx.x == g_tc_timeline_on - 1) g_tc_timeline_gate = (n_mb == 1 || m == n_mb - 2);   // a step WITH barrier 3
         tstamp(22);
         if (EPOCH && tid == 256) {    // Adam bias corrections of this step, off the critical path
@@ -838,7 +841,43 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             s_part[q][e] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
             __syncthreads();
             if (q == 0 && i < i1) {
-                const float g = (s_part[0][e] + s_part[1][e]) + (s_part[2][e] + s_part[3][e]);
+                float g = (s_part[0][e] + s_part[1][e]) + (s_part[2][e] + s_part[3][e]);
+                if (px.world > 1) {
+                    // ---- cross-GPU sum of this element over NVLink peer memory (fused all-reduce) -----------
+                    // push (value, seq) into every peer's receive slot of this rank, then gather the peers'
+                    // packets from the local buffer and add in rank order (bit-identical on every rank)
+                    const unsigned int seq = seq0 + (unsigned int)m + 1u;
+                    const size_t slot = (size_t)(seq & 1u) * (size_t)width + (size_t)i;
+                    const unsigned long long pkt = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(g);
+                    for (int r = 0; r < px.world; ++r) {
+                        if (r == px.rank) continue;
+                        unsigned long long* dst = px.recv[r] + (size_t)px.rank * 2u * (size_t)width + slot;
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(pkt) : "memory");
+                    }
+                    float sum = 0.0f;
+                    unsigned long long t_start = 0ull;
+                    for (int r = 0; r < px.world; ++r) {
+                        float v = g;
+                        if (r != px.rank) {
+                            const unsigned long long* src = px.recv[px.rank] + (size_t)r * 2u * (size_t)width + slot;
+                            unsigned long long got;
+                            unsigned int spins = 0u;
+                            for (;;) {
+                                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+                                if ((unsigned int)(got >> 32) == seq) break;
+                                if ((++spins & 0xffffu) == 0u) {      // a peer that never shows up must not hang the GPU
+                                    unsigned long long now;
+                                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                                    if (t_start == 0ull) t_start = now;
+                                    else if (now - t_start > 20000000000ull) __trap();
+                                }
+                            }
+                            v = __uint_as_float((unsigned int)got);
+                        }
+                        sum += v;
+                    }
+                    g = sum;
+                }
                 opt.grad_scratch[i] = g;
                 if (i < d.n_params) ss += (double)g * (double)g;
             }
@@ -916,7 +955,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
     if (EPOCH && tid == 0) {
-        if (blockIdx.x == 0) *opt.step_count = step0 + n_mb;
+        if (blockIdx.x == 0) {
+            *opt.step_count = step0 + n_mb;
+            if (px.world > 1) *px.hdr = seq0 + (unsigned int)n_mb;
+        }
         __threadfence();
         if (atomicAdd(&g_ep_depart, 1u) == gridDim.x - 1) {
             g_ep_arrive = 0u; g_ep_depart = 0u; g_ep_ss[0] = 0.0; g_ep_ss[1] = 0.0;
@@ -1137,7 +1179,7 @@ int launch_ppo_grad_tc(const float* params, const ts_actor_critic_desc& d, const
     const int64_t tiles = (hi - lo + kRows - 1) / kRows;
     const unsigned grid = (unsigned)imin(tiles, num_sms());
     ppo_tc_kernel<false><<<grid, kThreads, smem, st>>>(params, d, hp, obs, act, adv, ret, logp_old, v_s, perm, lo, hi - lo, hi, 1,
-                                                       global_rows, adv_moments, grad, AdamArgs{}, (uint8_t*)nullptr);
+                                                       global_rows, adv_moments, grad, AdamArgs{}, (uint8_t*)nullptr, PeerArgs{});
     return check_launch("ts_ppo_grad(tc)");
 }
 
@@ -1147,7 +1189,7 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
                         const float* act, const float* adv, const float* ret, const float* logp_old, const float* v_s,
                         const int32_t* perm, int64_t lo0, int64_t mb_size, int64_t end, int n_mb, const float* adv_moments,
                         float* partials, float* grad_scratch, float* exp_avg, float* exp_avg_sq, int64_t* step_count,
-                        float* stats, void* weight_image, cudaStream_t st) {
+                        float* stats, void* weight_image, const PeerArgs& px, cudaStream_t st) {
     const size_t smem = make_smem(d.obs_dim, 0).total;
     if (int e = configure_ppo_smem(smem)) return e;
     const int64_t last = end - (lo0 + (int64_t)(n_mb - 1) * mb_size);
@@ -1169,7 +1211,7 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
         if (int e = check_launch("ts_ppo_update(weight image)")) return e;
     }
     TS_CUDA(cudaLaunchKernelEx(&cfg, ppo_tc_kernel<true>, (const float*)params, d, hp, obs, act, adv, ret, logp_old, v_s, perm,
-                               lo0, mb_size, end, n_mb, zero, adv_moments, partials, opt, wimg));
+                               lo0, mb_size, end, n_mb, zero, adv_moments, partials, opt, wimg, px));
     return check_launch("ts_ppo_epoch(tc)");
 }
 
