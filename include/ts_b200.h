@@ -134,6 +134,12 @@ int ts_mark_members(const int64_t* idx, int64_t n, const int64_t* members,
 int ts_gather_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t n, void* dst,
                    ts_stream_t stream);
 
+/* dst[idx[p]] = src[p] for p < n, rows of row_bytes bytes: the device side of the asynchronous buffer mirror --
+ * ReplayBuffer.add (buffer_base.py:420-501, manager.py:131-198) writes one row per env at scattered slots; the
+ * rows arrive contiguously from pinned staging.  idx entries must be distinct. */
+int ts_scatter_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t n, void* dst,
+                    ts_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * (4) Sum tree for prioritized replay (f64 tree, bit-exact indices).
  * tree: double[2*bound], root at 1, leaves at [bound, bound+size) (data/utils/segtree.py:19-26).

@@ -65,6 +65,7 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_sample_all_indices": [_P, _I64, _P, _P, _P, _P, _I64, _P, _P],
     "ts_mark_members": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P],
     "ts_gather_rows": [_P, _I64, _P, _I64, _P, _P],
+    "ts_scatter_rows": [_P, _I64, _P, _I64, _P, _P],
     "ts_segtree_setitem": [_P, _I64, _P, _P, C.c_int, _I64, _P],
     "ts_segtree_reduce": [_P, _I64, _I64, _I64, _P, _P],
     "ts_segtree_prefix_sum_idx": [_P, _I64, _P, _I64, _P, _P],

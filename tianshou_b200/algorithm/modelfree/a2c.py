@@ -121,17 +121,23 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
                 raise UnsupportedModelError(f"fused update needs a dense '{k}' array in the buffer")
         n = len(buffer)
         full = n == buffer.maxsize and bool(np.all(buffer._ins == 0))
-        up = {
-            "obs": _upload(meta_host.obs, dev, torch.float32).reshape(buffer.maxsize, -1),
-            "act": _upload(meta_host.act, dev, torch.float32).reshape(buffer.maxsize, -1),
-            "rew": _upload(meta_host.rew, dev, torch.float64),
-            "terminated": _upload(meta_host.terminated, dev),
-            "truncated": _upload(meta_host.truncated, dev),
-        }
-        if buffer._save_obs_next:
-            up["obs_next"] = _upload(meta_host.obs_next, dev, torch.float32).reshape(buffer.maxsize, -1)
+        need = ("obs", "act", "rew", "terminated", "truncated", "done") + (("obs_next",) if buffer._save_obs_next else ())
+        mirrored = buffer.device_columns()      # kept up to date by add(): no bulk transfer (data/buffer/mirror.py)
+        if mirrored is not None and all(k in mirrored for k in need) and mirrored["obs"].device == dev:
+            up = {k: mirrored[k] for k in need if k != "done"}
+            done_dev = mirrored["done"]
+        else:       # one DMA per key from the (pinned) host arrays
+            up = {"obs": _upload(meta_host.obs, dev, torch.float32), "act": _upload(meta_host.act, dev, torch.float32),
+                  "rew": _upload(meta_host.rew, dev, torch.float64), "terminated": _upload(meta_host.terminated, dev),
+                  "truncated": _upload(meta_host.truncated, dev)}
+            if buffer._save_obs_next:
+                up["obs_next"] = _upload(meta_host.obs_next, dev, torch.float32)
+            done_dev = _upload(meta_host.done, dev)
+        for k in ("obs", "act", "obs_next"):
+            if k in up:
+                up[k] = up[k].reshape(buffer.maxsize, -1)
         meta = ops.DeviceBufferMeta(
-            to_device(buffer._extend_offset, dev), _upload(meta_host.done, dev),
+            to_device(buffer._extend_offset, dev), done_dev,
             to_device(buffer.last_index, dev), to_device(buffer._sizes, dev))
         if full:
             indices = torch.arange(n, dtype=torch.int64, device=dev)

@@ -221,6 +221,17 @@ __global__ void gather_rows_kernel(const W* __restrict__ src, int64_t row_words,
         dst[t] = src[idx[p] * row_words + w];
     }
 }
+// inverse: dst[idx[p]] = src[p] (device mirror of ReplayBuffer.add: rows staged contiguously, slots scattered)
+template <typename W>
+__global__ void scatter_rows_kernel(const W* __restrict__ src, int64_t row_words,
+                                    const int64_t* __restrict__ idx, int64_t n, W* __restrict__ dst) {
+    const int64_t total = n * row_words;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = t / row_words, w = t - p * row_words;
+        dst[idx[p] * row_words + w] = src[t];
+    }
+}
 __global__ void gather_bytes_kernel(const uint8_t* __restrict__ src, const int64_t* __restrict__ idx,
                                     int64_t n, uint8_t* __restrict__ dst) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,6 +370,27 @@ extern "C" int ts_gather_rows(const void* src, int64_t row_bytes, const int64_t*
         gather_rows_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), row_bytes, idx, n, static_cast<uint8_t*>(dst));
     }
     return tsb::check_launch("ts_gather_rows");
+}
+
+extern "C" int ts_scatter_rows(const void* src, int64_t row_bytes, const int64_t* idx, int64_t n,
+                               void* dst, ts_stream_t stream) {
+    if (n == 0 || row_bytes == 0) return 0;
+    TS_REQUIRE(src && idx && dst, "ts_scatter_rows: null pointer");
+    cudaStream_t st = tsb::as_stream(stream);
+    const bool a16 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+    if (row_bytes % 16 == 0 && a16) {
+        const int64_t rw = row_bytes / 16;
+        const unsigned grid = (unsigned)tsb::imin((int64_t)blocks_for(n * rw, 256), 148 * 32);
+        scatter_rows_kernel<uint4><<<grid, 256, 0, st>>>(static_cast<const uint4*>(src), rw, idx, n, static_cast<uint4*>(dst));
+    } else if (row_bytes % 4 == 0 && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0)) {
+        const int64_t rw = row_bytes / 4;
+        const unsigned grid = (unsigned)tsb::imin((int64_t)blocks_for(n * rw, 256), 148 * 32);
+        scatter_rows_kernel<uint32_t><<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(src), rw, idx, n, static_cast<uint32_t*>(dst));
+    } else {
+        const unsigned grid = (unsigned)tsb::imin((int64_t)blocks_for(n * row_bytes, 256), 148 * 32);
+        scatter_rows_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(src), row_bytes, idx, n, static_cast<uint8_t*>(dst));
+    }
+    return tsb::check_launch("ts_scatter_rows");
 }
 
 extern "C" int ts_narrow_i64_i32(const int64_t* src, int64_t n, int32_t* dst, ts_stream_t stream) {

@@ -108,8 +108,10 @@ class ReplayBuffer:
         sample_avail: bool = False,
         random_seed: int = 42,
         device: torch.device | str | None = None,
+        device_mirror: bool = False,
         **kwargs: Any,
     ) -> None:
+        self.__dict__["_device_mirror_arg"] = bool(device_mirror)
         self.options: dict[str, Any] = {
             "stack_num": stack_num,
             "ignore_obs_next": ignore_obs_next,
@@ -142,6 +144,8 @@ class ReplayBuffer:
         d["_mirror"] = None
         d["_mirror_version"] = -1
         d["_version"] = 0
+        d["_dmirror"] = None            # asynchronous device copy of the transition arrays (mirror.py)
+        d.setdefault("_device_mirror_arg", False)
         self._reset_state(keep_statistics=False)
 
     def _reset_state(self, keep_statistics: bool) -> None:
@@ -199,6 +203,7 @@ class ReplayBuffer:
         state["_pinned"] = []
         state["_mirror"] = None
         state["_mirror_version"] = -1
+        state["_dmirror"] = None
         return state
 
     def __setstate__(self, state: dict[str, Any]) -> None:
@@ -226,6 +231,31 @@ class ReplayBuffer:
 
     def _touch(self) -> None:
         self.__dict__["_version"] += 1
+
+    # asynchronous device mirror of the transition arrays (opt-in: ``device_mirror=True``)
+    def enable_device_mirror(self) -> None:
+        """Keep a device copy of obs / act / rew / flags / obs_next up to date from ``add()`` on (mirror.py)."""
+        self.__dict__["_device_mirror_arg"] = True
+
+    def _mirror_add(self, idx: np.ndarray, batch: Batch) -> None:
+        if not self._device_mirror_arg:
+            return
+        if self._dmirror is None:
+            from .mirror import DeviceMirror
+            self.__dict__["_dmirror"] = DeviceMirror(self)
+        self._dmirror.push(np.asarray(idx, dtype=np.int64).reshape(-1), batch)
+
+    def device_columns(self) -> "dict[str, torch.Tensor] | None":
+        """Device-resident transition arrays if the mirror is enabled and reflects the host buffer, else None."""
+        return self._dmirror.columns() if self._dmirror is not None else None
+
+    def sync_device_mirror(self) -> None:
+        """Re-upload everything (after edits that bypass ``add()``, e.g. in-place numpy writes)."""
+        if self._device_mirror_arg and len(self._meta.get_keys()) > 0:
+            if self._dmirror is None:
+                from .mirror import DeviceMirror
+                self.__dict__["_dmirror"] = DeviceMirror(self)
+            self._dmirror.resync()
 
     # ------------------------------------------------------------------ index API (CUDA)
     def unfinished_index(self) -> np.ndarray:
@@ -340,6 +370,7 @@ class ReplayBuffer:
             batch.truncated = batch.truncated.astype(bool)
             self._allocate(batch, stack=not stacked)
             self._meta[idx] = batch
+        self._mirror_add(idx, batch)
         return idx, ep_ret, ep_len, ep_start
 
     def update(self, buffer: "ReplayBuffer") -> np.ndarray:
@@ -364,6 +395,8 @@ class ReplayBuffer:
 
     def reset(self, keep_statistics: bool = False) -> None:
         self._reset_state(keep_statistics)
+        if self._dmirror is not None:
+            self._dmirror.on_reset()
 
     def set_batch(self, batch: Batch) -> None:
         assert len(batch) == self.maxsize and set(batch.get_keys()).issubset(self._reserved_keys), (
@@ -491,6 +524,7 @@ class ReplayBuffer:
     def set_array_at_key(self, seq: np.ndarray, key: str, index: IndexType | None = None,
                          default_value: float | None = None) -> None:
         self._meta.set_array_at_key(seq, key, index, default_value)
+        self._touch()
 
     def hasnull(self) -> bool:
         return self[:].hasnull()
@@ -572,6 +606,7 @@ class ReplayBufferManager(ReplayBuffer):
             batch.truncated = batch.truncated.astype(bool)
             self._allocate(batch, stack=False)
             self._meta[idx] = batch
+        self._mirror_add(idx, batch)
         return idx, ep_ret, ep_len, ep_start
 
     def _child_rng(self, e: int) -> np.random.RandomState:
@@ -623,5 +658,6 @@ class VectorReplayBuffer(ReplayBufferManager):
         assert buffer_num > 0
         size = int(np.ceil(total_size / buffer_num))
         probe = ReplayBuffer(size, **kwargs)
+        self.__dict__["_device_mirror_arg"] = probe._device_mirror_arg
         self._setup(np.full(buffer_num, size, dtype=np.int64), probe._random_seed, probe._device_arg,
                     probe.options)
