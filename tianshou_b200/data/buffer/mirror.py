@@ -99,8 +99,10 @@ class DeviceMirror:
             slot["event"].synchronize()     # the staging memory of this slot is free again (normally long ago)
         slot["host"]["_idx"][:n].numpy()[...] = idx
         for k in self.cols:
-            np.copyto(slot["host"][k][:n].numpy(), np.asarray(batch[k])[:n].reshape(slot["host"][k][:n].shape),
-                      casting="unsafe")
+            dst = slot["host"][k][:n].numpy()
+            a = np.asarray(batch[k])
+            a = a.reshape(dst.shape) if a.size == dst.size else a[:n].reshape(dst.shape)   # un-stacked single transition
+            np.copyto(dst, a, casting="unsafe")
         with torch.cuda.stream(self.stream):
             slot["dev"]["_idx"][:n].copy_(slot["host"]["_idx"][:n], non_blocking=True)
             for k, dst in self.cols.items():
