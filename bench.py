@@ -443,8 +443,9 @@ def main() -> None:
         "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / K},
         "e2e_numpy_rng": {"value": e2e_np_value, "unit": "transitions/s", "ms_per_step": ms_np / n_np,
-                          "note": "public API with minibatch_shuffle='numpy': np.random.permutation per repeat on the host "
-                                  "(bit-identical minibatch composition to the reference)"},
+                          "note": "public API with the default minibatch_shuffle='numpy': the reference's np.random.permutation draw per "
+                                  "pass (global MT19937 stream, bit-identical minibatch composition) generated on the host by "
+                                  "ts_host_mt19937_permutation -- host-bound at ~4 ms per 524288-element permutation"},
         "gpu_launches": int(launches),
         "ingest": ingest,
         "roofline": {"kernel": "ppo_tc_kernel<EPOCH> (persistent: every optimiser step of one pass = minibatch fwd/bwd + "

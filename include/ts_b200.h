@@ -329,6 +329,13 @@ int ts_ppo_epoch_multi(float* params, float* grad, float* partials, float* exp_a
                        void* weight_image, float* stats, int32_t rank, int32_t world,
                        void* const* peer_buffers /* host */, ts_stream_t stream);
 
+/* HOST function (no device work): out[0..n) = np.random.permutation(n) for numpy's legacy MT19937 RandomState whose
+ * state is (key[624], *pos) -- the draw Batch.split makes once per pass (batch.py:1209).  Bit-identical to numpy
+ * (MT19937 + random_interval masked rejection + backward Fisher-Yates of RandomState.shuffle); key / *pos are
+ * advanced exactly as numpy would, so writing them back with np.random.set_state keeps the global stream in step.
+ * Writes int32 directly (e.g. into the pinned upload buffer). */
+int ts_host_mt19937_permutation(uint32_t* key /* in/out */, int32_t* pos /* in/out */, int64_t n, int32_t* out);
+
 /* Device-side minibatch order (opt-in alternative to np.random.permutation, batch.py:1209):
  * out[r*n + i] = pi_r(i), pi_r a keyed bijection of [0,n) (cycle-walking Feistel/Philox). */
 int ts_make_permutation(uint64_t seed, int32_t first_epoch, int32_t n_epochs, int64_t n,

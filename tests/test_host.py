@@ -161,3 +161,19 @@ def test_cabi_struct_layouts_match_header():
     from tianshou_b200._cabi import ActorCriticDesc, PPOHParams
     assert ctypes.sizeof(ActorCriticDesc) == 4 * 4 + 14 * 8
     assert ctypes.sizeof(PPOHParams) == 11 * 8 + 3 * 4 + 4      # trailing pad to 8
+
+
+def test_host_permutation_is_numpy_global_permutation_bit_for_bit():
+    """The product path's minibatch order == np.random.permutation on the global stream (batch.py:1209),
+    including the RNG state it leaves behind."""
+    import torch
+
+    from tianshou_b200.data.batch import numpy_global_permutation_
+    for seed, n in [(0, 1), (1, 2), (2, 7), (3, 1000), (4, 65537), (5, 524288)]:
+        np.random.seed(seed)
+        ref = np.random.permutation(n)
+        ref_next = np.random.rand(3)
+        np.random.seed(seed)
+        out = numpy_global_permutation_(torch.empty(n, dtype=torch.int32))
+        assert np.array_equal(out.numpy(), ref), (seed, n)
+        assert np.array_equal(np.random.rand(3), ref_next)     # the global stream continues identically

@@ -42,7 +42,7 @@ def test_gae_vs_reference_outputs():
         np.testing.assert_allclose(adv.cpu().numpy(), g[p + "adv"], rtol=1e-11, atol=1e-11)
 
 
-@pytest.mark.parametrize("n", [1, 7, 8, 2047, 2048, 2049, 10_000, 4096 * 128])
+@pytest.mark.parametrize("n", [1, 7, 8, 2047, 2048, 2049, 10_000, 4096 * 128, 8192 * 256])   # ... C2, C5 (BASELINE configs[1], [4])
 @pytest.mark.parametrize("vdtype", [np.float32, np.float64])
 def test_gae_sizes_vs_oracle(n, vdtype):
     rng = np.random.default_rng(n)

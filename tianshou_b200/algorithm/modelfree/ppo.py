@@ -27,7 +27,7 @@ import torch
 from ... import ops
 from ..._cabi import STATS_STRIDE, call, ptr, stream_ptr
 from ...data import Batch, ReplayBuffer
-from ...data.batch import minibatch_bounds
+from ...data.batch import minibatch_bounds, numpy_global_permutation_
 from ...parallel import allreduce_sum_, shard_bounds, world
 from ..optim import OptimizerFactory
 from .a2c import A2CTrainingStats, ActorCriticOnPolicyAlgorithm
@@ -90,6 +90,12 @@ class PPO(ActorCriticOnPolicyAlgorithm):
         batch.__dict__["logp_old"] = logp_old
         return batch
 
+    def _host_perm_rows(self, repeat: int, n: int) -> torch.Tensor:
+        t = self._scratch.get("host_perms")
+        if t is None or t.shape[0] < repeat or t.shape[1] != n:
+            t = self._scratch["host_perms"] = torch.empty((repeat, n), dtype=torch.int32, pin_memory=True)
+        return t
+
     def _ppo_hparams(self):
         return self._hparams(
             eps_clip=float(self.eps_clip), dual_clip=float(self.dual_clip or 0.0), vf_coef=float(self.vf_coef),
@@ -127,11 +133,11 @@ class PPO(ActorCriticOnPolicyAlgorithm):
                 if self.recompute_adv and r > 0:
                     self._add_returns_and_advantages(batch, None, None)
                 if perms is None:
-                    # the reference's RNG draw, overlapped with the GPU work enqueued so far
-                    order = np.random.permutation(N).astype(np.int32)
-                    host_perm = torch.from_numpy(order)
-                    if torch.cuda.is_available():
-                        host_perm = host_perm.pin_memory()
+                    # the reference's RNG draw (np.random.permutation on the global stream, batch.py:1209),
+                    # bit-identical, generated straight into pinned memory and overlapped with the GPU work
+                    # enqueued so far; one pinned row per pass so that a pending async copy is never overwritten
+                    host_perm = self._host_perm_rows(repeat, N)[r]
+                    numpy_global_permutation_(host_perm)
                     perm_r = host_perm.to(dev, non_blocking=True)
                 else:
                     perm_r = perms[r]

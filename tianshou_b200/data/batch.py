@@ -707,3 +707,23 @@ def minibatch_bounds(n: int, size: int, merge_last: bool) -> list[tuple[int, int
             break
         out.append((lo, min(lo + size, n)))
     return out
+
+
+def numpy_global_permutation_(out: "torch.Tensor") -> "torch.Tensor":
+    """``out[:] = np.random.permutation(len(out))`` (int32, host tensor -- typically pinned) drawn from numpy's
+    GLOBAL legacy RandomState exactly as ``Batch.split(shuffle=True)`` does (batch.py:1209): same values, same
+    state afterwards.  Runs the reference's algorithm (MT19937 + masked rejection + backward Fisher-Yates) as a
+    tight int32 loop in the C library (``ts_host_mt19937_permutation``), ~3x faster than numpy + astype + copy."""
+    import ctypes as C
+
+    from .._cabi import call
+    n = out.numel()
+    st = np.random.get_state()
+    if st[0] != "MT19937" or out.dtype != torch.int32 or out.is_cuda or not out.is_contiguous():
+        out.copy_(torch.from_numpy(np.random.permutation(n).astype(np.int32)))
+        return out
+    key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(st[2]))
+    call("ts_host_mt19937_permutation", key.ctypes.data_as(C.c_void_p), C.byref(pos), n, C.c_void_p(out.data_ptr()))
+    np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+    return out
