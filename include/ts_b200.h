@@ -230,8 +230,10 @@ typedef struct ts_ppo_hparams {
  * advantage_normalization, else NULL.  perm may be NULL (identity). */
 int32_t ts_ppo_partial_rows(void);
 
-/* Bytes of the optional `weight_image` scratch of ts_ppo_update: both networks' weights pre-split into the
- * bf16x3 tensor-core operand layout, so that a CTA stages a network with one bulk copy.  0 when the network
+/* Bytes of the optional `weight_image` scratch of ts_ppo_update: a 128-byte control block (grid-barrier state of
+ * the persistent kernel: must be ZERO when first used and is left zero by every launch; one scratch per model, never
+ * shared by two updates in flight) followed by both networks' weights pre-split into the bf16x3 tensor-core operand
+ * layout, so that a CTA stages a network with one bulk copy.  0 when the network
  * shape is not covered by the tensor-core kernels (pass NULL then). */
 int64_t ts_ppo_weight_image_bytes(const ts_actor_critic_desc* desc);
 int ts_ppo_grad(const float* params, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,

@@ -523,9 +523,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // State of the in-kernel grid barriers of the fused epoch kernel (self-resetting; launches are
 // stream-ordered and every CTA of the grid is resident: cooperative launch, 1 CTA / SM).
-__device__ unsigned int g_ep_arrive = 0u;
-__device__ unsigned int g_ep_depart = 0u;
-__device__ double g_ep_ss[2] = {0.0, 0.0};
+// They live in the 128-byte control block in front of the caller's weight image (one per model instance, so
+// two models updating on different streams never share barrier state); without an image: this global block.
+struct EpochCtl {
+    unsigned int arrive, depart;
+    double ss[2];
+};
+constexpr size_t kCtlBytes = 128;
+__device__ EpochCtl g_ep_ctl = {0u, 0u, {0.0, 0.0}};
 
 struct AdamArgs {     // optimiser half of the fused single-GPU path
     float* params_w;
@@ -538,6 +543,7 @@ struct AdamArgs {     // optimiser half of the fused single-GPU path
 
 struct GridBarrier {   // monotonic counter: the k-th use waits for k * gridDim.x arrivals
     unsigned int target;
+    unsigned int* ctr;
     // Split phase.  arrive(): release at gpu scope (cumulative over the bar.sync) -- a release waits for the
     // calling thread's OUTSTANDING LOADS too, so prefetches that should fly across the barrier are issued
     // between arrive() and wait().
@@ -545,14 +551,14 @@ struct GridBarrier {   // monotonic counter: the k-th use waits for k * gridDim.
         __syncthreads();
         if (threadIdx.x == 0) {
             target += gridDim.x;
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&g_ep_arrive) : "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         }
     }
     __device__ __forceinline__ void wait() {
         if (threadIdx.x == 0) {
             unsigned int seen;
             do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&g_ep_arrive) : "memory");
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
             } while (seen < target);
         }
         __syncthreads();
@@ -620,7 +626,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
     Pipe pipe{&s_bar, 0u};
-    GridBarrier gbar{0u};
+    EpochCtl* ctl = wimg != nullptr ? reinterpret_cast<EpochCtl*>(wimg - kCtlBytes) : &g_ep_ctl;
+    GridBarrier gbar{0u, &ctl->arrive};
     // Weight staging.  With a weight image: one bulk copy (TMA engine) per network, issued as early as the
     // block is dead, completion on s_wbar.  Without: gather + split in the CTA (stage_weights).
     uint32_t wphase = 0u;
@@ -807,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         const int64_t i1 = tsb::imin(i0 + slice, width);
         const int e = tid & 127, q = tid >> 7;
         const int64_t step = step0 + m + 1;
-        double* ss_cur = &g_ep_ss[m & 1];
+        double* ss_cur = &ctl->ss[m & 1];
         tstamp(10);
         // gathers of this CTA's tile of the next minibatch: in flight across the barrier
         TileIn pin;
@@ -908,7 +915,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
                 coef = fminf(coef, 1.0f);
             }
             s_coef = coef; s_norm = total_norm;
-            if (blockIdx.x == 0) g_ep_ss[(m + 1) & 1] = 0.0;       // next step's accumulator (idle until barrier 3)
+            if (blockIdx.x == 0) ctl->ss[(m + 1) & 1] = 0.0;       // next step's accumulator (idle until barrier 3)
         }
         __syncthreads();
         const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
@@ -960,8 +967,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             if (px.world > 1) *px.hdr = seq0 + (unsigned int)n_mb;
         }
         __threadfence();
-        if (atomicAdd(&g_ep_depart, 1u) == gridDim.x - 1) {
-            g_ep_arrive = 0u; g_ep_depart = 0u; g_ep_ss[0] = 0.0; g_ep_ss[1] = 0.0;
+        if (atomicAdd(&ctl->depart, 1u) == gridDim.x - 1) {
+            ctl->arrive = 0u; ctl->depart = 0u; ctl->ss[0] = 0.0; ctl->ss[1] = 0.0;
             __threadfence();
         }
     }
@@ -1203,7 +1210,8 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int64_t zero = 0;
-    uint8_t* wimg = static_cast<uint8_t*>(weight_image);
+    // scratch layout: [128-byte control block (grid-barrier state, zero between launches)][critic block][actor block]
+    uint8_t* wimg = weight_image ? static_cast<uint8_t*>(weight_image) + kCtlBytes : nullptr;
     if (wimg) {   // (re)build the pre-split image from the current parameters: the host may have changed them
         const Smem S = make_smem(d.obs_dim, 0);
         TS_CUDA(cudaMemsetAsync(wimg, 0, 2 * (size_t)S.wblk_bytes, st));
@@ -1215,7 +1223,9 @@ int launch_ppo_epoch_tc(float* params, const ts_actor_critic_desc& d, const ts_p
     return check_launch("ts_ppo_epoch(tc)");
 }
 
-int64_t weight_image_bytes(const ts_actor_critic_desc& d) { return tc_supported(d) ? 2 * (int64_t)make_smem(d.obs_dim, 0).wblk_bytes : 0; }
+int64_t weight_image_bytes(const ts_actor_critic_desc& d) {
+    return tc_supported(d) ? (int64_t)kCtlBytes + 2 * (int64_t)make_smem(d.obs_dim, 0).wblk_bytes : 0;
+}
 
 int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
                       const float* in1, float* out1, int64_t n, cudaStream_t st) {
