@@ -176,12 +176,24 @@ int ts_prio_get_weight(const double* tree, int64_t bound, const int64_t* index, 
  * and continuous.py:144-169,220-238.
  * All parameters live in ONE flat f32 buffer in torch layout ([out][in] row-major weights);
  * offsets are in floats.  The same offsets index the flat gradient / Adam-moment buffers.
+ *
+ * Variants selected by `flags` (the reference's discrete PPO test net, test/discrete/test_ppo_discrete.py:90-100:
+ * ONE Net(obs -> 64 -> 64, ReLU) shared by DiscreteActor(softmax_output=True) and DiscreteCritic,
+ * utils/net/discrete.py:29-123, policy distribution torch.distributions.Categorical(probs)):
+ *   TS_AC_RELU         hidden activation max(x, 0) instead of tanh (Net's default, common.py MLP);
+ *   TS_AC_CATEGORICAL  head = act_dim logits -> softmax -> Categorical; a_logstd is unused (-1); the
+ *                      action array holds ONE index per row, stored as f32 (ppo.py:156 casts it so).
+ * A SHARED trunk is expressed by aliased offsets (c_w1 == a_w1, c_b1 == a_b1, c_w2 == a_w2, c_b2 == a_b2): the
+ * shared parameters are counted once in n_params and both losses' gradients add into the same slots.
+ * Variants with flags != 0 or a shared trunk run the fp32 SIMT kernels.
  * ------------------------------------------------------------------------------------------ */
+#define TS_AC_RELU 1
+#define TS_AC_CATEGORICAL 2
 typedef struct ts_actor_critic_desc {
     int32_t obs_dim;  /* <= 64 */
     int32_t act_dim;  /* <= 16 */
     int32_t hidden;   /* 64 */
-    int32_t reserved;
+    int32_t flags;           /* TS_AC_* bits; 0 = tanh trunks + diagonal-Gaussian head */
     int64_t a_w1, a_b1, a_w2, a_b2, a_w3, a_b3, a_logstd; /* actor: W1[h][obs] .. W3[act][h], logstd[act] */
     int64_t c_w1, c_b1, c_w2, c_b2, c_w3, c_b3;           /* critic: .. W3[1][h], b3[1] */
     int64_t n_params;
@@ -193,7 +205,9 @@ int ts_critic_forward(const float* params, const ts_actor_critic_desc* desc /* h
                       const float* obs0, float* v_out0, const float* obs1, float* v_out1,
                       int64_t n, ts_stream_t stream);
 /* logp_out[r] = Independent(Normal(mu(obs[r]), exp(logstd)), 1).log_prob(act[r])
- * (ppo.py:157-161 with reinforce.py:167-192).  mu_out (n*act_dim, nullable) receives mu. */
+ * (ppo.py:157-161 with reinforce.py:167-192).  mu_out (n*act_dim, nullable) receives mu.
+ * TS_AC_CATEGORICAL: logp_out[r] = Categorical(probs = softmax(logits(obs[r]))).log_prob(act[r]) with act one f32
+ * index per row; mu_out receives the probabilities (the actor's output). */
 int ts_actor_logp(const float* params, const ts_actor_critic_desc* desc /* host */,
                   const float* obs, const float* act, int64_t n, float* logp_out, float* mu_out,
                   ts_stream_t stream);

@@ -362,8 +362,144 @@ def gen_ppo():
         print(f"ppo_ref_{name}.npz", len(out), "arrays; gradient_steps", int(out["u0_gradient_steps"]))
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[0]: the reference's own discrete PPO test network (test/discrete/test_ppo_discrete.py:90-125):
+# ONE Net(obs -> 64 -> 64, ReLU) shared by DiscreteActor(softmax_output=True) and DiscreteCritic,
+# orthogonal init, Categorical(probs), CartPole shapes (obs 4, 2 actions).
+def build_ref_ppo_discrete(obs_dim, n_act, seed, shared=True, **ppo_kw):
+    from gymnasium.spaces import Discrete
+    from tianshou.algorithm.modelfree.reinforce import DiscreteActorPolicy
+    from tianshou.utils.net.common import ActorCritic
+    from tianshou.utils.net.discrete import DiscreteActor, DiscreteCritic
+    torch.manual_seed(seed)
+    net = Net(state_shape=(obs_dim,), hidden_sizes=(64, 64))
+    net_c = net if shared else Net(state_shape=(obs_dim,), hidden_sizes=(64, 64))
+    actor = DiscreteActor(preprocess_net=net, action_shape=(n_act,))
+    critic = DiscreteCritic(preprocess_net=net_c)
+    for m in ActorCritic(actor, critic).modules():
+        if isinstance(m, torch.nn.Linear):
+            torch.nn.init.orthogonal_(m.weight)
+            torch.nn.init.zeros_(m.bias)
+    policy = DiscreteActorPolicy(actor=actor, dist_fn=torch.distributions.Categorical, action_space=Discrete(n_act),
+                                 deterministic_eval=True)
+    lr = ppo_kw.pop("lr", 3e-4)
+    algo = PPO(policy=policy, critic=critic, optim=AdamOptimizerFactory(lr=lr), **ppo_kw)
+    return algo, actor, critic
+
+
+def discrete_named_params(actor, critic):
+    t1, t2 = [m for m in actor.preprocess.model.model if isinstance(m, torch.nn.Linear)]
+    c1, c2 = [m for m in critic.preprocess.model.model if isinstance(m, torch.nn.Linear)]
+    a3, c3 = actor.last.model[0], critic.last.model[0]
+    d = {"a_w1": t1.weight, "a_b1": t1.bias, "a_w2": t2.weight, "a_b2": t2.bias, "a_w3": a3.weight, "a_b3": a3.bias}
+    if c1 is not t1:
+        d.update({"c_w1": c1.weight, "c_b1": c1.bias, "c_w2": c2.weight, "c_b2": c2.bias})
+    d.update({"c_w3": c3.weight, "c_b3": c3.bias})
+    return d
+
+
+def synth_rollout_discrete(rng, E, steps, obs_dim, n_act, p_term, trunc_len):
+    """CartPole-shaped: obs f64 (gymnasium's CartPole returns float32; the buffer keeps what it gets), integer
+    actions, reward 1.0 per step."""
+    t_in_ep = np.zeros(E, dtype=np.int64)
+    obs = rng.standard_normal((E, obs_dim)).astype(np.float32)
+    out = []
+    for _ in range(steps):
+        act = rng.integers(0, n_act, E)
+        rew = np.ones(E) + 0.1 * rng.standard_normal(E)
+        obs_next = (obs + 0.1 * rng.standard_normal((E, obs_dim))).astype(np.float32)
+        term = rng.random(E) < p_term
+        t_in_ep += 1
+        trunc = (t_in_ep >= trunc_len) & ~term
+        out.append(dict(obs=obs, act=act, rew=rew, terminated=term, truncated=trunc, obs_next=obs_next))
+        done = term | trunc
+        t_in_ep[done] = 0
+        fresh = rng.standard_normal((E, obs_dim)).astype(np.float32)
+        obs = np.where(done[:, None], fresh, obs_next)
+    return out
+
+
+def gen_ppo_discrete():
+    import tianshou.algorithm.modelfree.ppo as ref_ppo
+    variants = {
+        # the reference test's hyper-parameters (test_ppo_discrete.py:28-63) on 10 envs (BASELINE configs[0])
+        "C1": dict(E=10, cap=40, steps=40, bs=64, repeat=3, seed=0, shared=True,
+                   kw=dict(gamma=0.99, gae_lambda=0.95, max_grad_norm=0.5, vf_coef=0.5, ent_coef=0.0,
+                           return_scaling=False, eps_clip=0.2, value_clip=False, dual_clip=None,
+                           advantage_normalization=False, recompute_advantage=False)),
+        # every optional term on (entropy bonus, advantage normalisation, value clip, dual clip, return scaling)
+        "C1b": dict(E=8, cap=24, steps=30, bs=50, repeat=2, seed=1, shared=True,
+                    kw=dict(gamma=0.98, gae_lambda=0.9, max_grad_norm=0.5, vf_coef=0.25, ent_coef=0.01,
+                            return_scaling=True, eps_clip=0.2, value_clip=True, dual_clip=3.0,
+                            advantage_normalization=True, recompute_advantage=True, lr=1e-3)),
+        # separate trunks
+        "C1c": dict(E=6, cap=20, steps=20, bs=None, repeat=2, seed=2, shared=False,
+                    kw=dict(gamma=0.99, gae_lambda=0.95, max_grad_norm=None, vf_coef=0.5, ent_coef=0.005,
+                            return_scaling=False, eps_clip=0.2, value_clip=False, dual_clip=None,
+                            advantage_normalization=False, recompute_advantage=False)),
+    }
+    obs_dim, n_act = 4, 2
+    for name, cfg in variants.items():
+        rng = np.random.default_rng(300 + cfg["seed"])
+        algo, actor, critic = build_ref_ppo_discrete(obs_dim, n_act, cfg["seed"], shared=cfg["shared"], **dict(cfg["kw"]))
+        steps = synth_rollout_discrete(rng, cfg["E"], cfg["steps"], obs_dim, n_act, 0.04, 25)
+        buf = VectorReplayBuffer(cfg["E"] * cfg["cap"], cfg["E"])
+        fill(buf, steps)
+        out = {"p0_" + k: v.detach().numpy().copy() for k, v in discrete_named_params(actor, critic).items()}
+        steps2 = synth_rollout_discrete(rng, cfg["E"], cfg["steps"], obs_dim, n_act, 0.04, 25)
+        captured = {"pre": [], "seq": []}
+        orig_pre = algo._preprocess_batch
+
+        def pre_hook(batch, buffer, indices, orig_pre=orig_pre, captured=captured):
+            b = orig_pre(batch, buffer, indices)
+            captured["pre"].append({k: b[k].detach().numpy().copy() for k in ("v_s", "returns", "adv", "logp_old")}
+                                   | {"indices": np.asarray(indices).copy()})
+            return b
+
+        algo._preprocess_batch = pre_hook
+        orig_from = ref_ppo.SequenceSummaryStats.from_sequence
+
+        def rec(seq, orig_from=orig_from, captured=captured):
+            captured["seq"].append(np.asarray(seq, dtype=np.float64))
+            return orig_from(seq)
+
+        ref_ppo.SequenceSummaryStats.from_sequence = rec
+        for u, st in enumerate([steps, steps2]):
+            if u == 1:
+                buf.reset(keep_statistics=True)
+                fill(buf, st)
+            np.random.seed(1000 + u)
+            torch.manual_seed(2000 + u)
+            N = len(buf)
+            with policy_within_training_step(algo.policy):
+                stats = algo.update(buffer=buf, batch_size=cfg["bs"], repeat=cfg["repeat"])
+            np.random.seed(1000 + u)
+            perms = np.stack([np.random.permutation(N) for _ in range(cfg["repeat"])])
+            pre = captured["pre"][u]
+            seqs = captured["seq"][4 * u: 4 * u + 4]
+            o = f"u{u}_"
+            out.update({o + "perms": perms, o + "indices": pre["indices"], o + "v_s": pre["v_s"],
+                        o + "returns": pre["returns"], o + "adv": pre["adv"], o + "logp_old": pre["logp_old"],
+                        o + "losses": np.stack(seqs, axis=1), o + "gradient_steps": stats.gradient_steps,
+                        o + "rms": np.array([float(algo.ret_rms.mean), float(algo.ret_rms.var), float(algo.ret_rms.count)])})
+            out.update({o + "p_" + k: v.detach().numpy().copy() for k, v in discrete_named_params(actor, critic).items()})
+            for key in ("obs", "act", "rew", "terminated", "truncated", "obs_next", "done"):
+                out[o + "buf_" + key] = np.asarray(buf._meta[key]).copy()
+            out.update({o + "meta_" + k: v for k, v in meta_of(buf).items()})
+            out[o + "unfinished"] = buf.unfinished_index()
+        ref_ppo.SequenceSummaryStats.from_sequence = orig_from
+        out["cfg_E"], out["cfg_cap"], out["cfg_steps"] = cfg["E"], cfg["cap"], cfg["steps"]
+        out["cfg_bs"] = -1 if cfg["bs"] is None else cfg["bs"]
+        out["cfg_repeat"], out["cfg_shared"] = cfg["repeat"], int(cfg["shared"])
+        for k, v in cfg["kw"].items():
+            out["kw_" + k] = np.nan if v is None else v
+        np.savez_compressed(os.path.join(OUT, f"ppo_ref_{name}.npz"), **out)
+        print(f"ppo_ref_{name}.npz", len(out), "arrays; gradient_steps", int(out["u0_gradient_steps"]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["returns", "index", "segtree", "ppo"]
+    which = sys.argv[1:] or ["returns", "index", "segtree", "ppo", "ppo_discrete"]
     for w in which:
-        {"returns": gen_returns, "index": gen_index, "segtree": gen_segtree, "ppo": gen_ppo}[w]()
+        {"returns": gen_returns, "index": gen_index, "segtree": gen_segtree, "ppo": gen_ppo,
+         "ppo_discrete": gen_ppo_discrete}[w]()

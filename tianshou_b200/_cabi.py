@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libts_b200.so")
 
 TS_F32, TS_F64 = 0, 1
+AC_RELU, AC_CATEGORICAL = 1, 2
 STATS_STRIDE = 8
 GRAD_EXTRA = 4
 
@@ -27,7 +28,7 @@ class ExtensionMissingError(RuntimeError):
 
 class ActorCriticDesc(C.Structure):
     _fields_ = [
-        ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("hidden", C.c_int32), ("reserved", C.c_int32),
+        ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("hidden", C.c_int32), ("flags", C.c_int32),
         ("a_w1", C.c_int64), ("a_b1", C.c_int64), ("a_w2", C.c_int64), ("a_b2", C.c_int64),
         ("a_w3", C.c_int64), ("a_b3", C.c_int64), ("a_logstd", C.c_int64),
         ("c_w1", C.c_int64), ("c_b1", C.c_int64), ("c_w2", C.c_int64), ("c_b2", C.c_int64),

@@ -2,12 +2,12 @@ from .base import Algorithm, OffPolicyAlgorithm, OnPolicyAlgorithm, Policy, Trai
 from .flat_params import UnsupportedModelError
 from .modelfree.a2c import A2CTrainingStats, ActorCriticOnPolicyAlgorithm
 from .modelfree.ppo import PPO
-from .modelfree.reinforce import ProbabilisticActorPolicy
+from .modelfree.reinforce import DiscreteActorPolicy, ProbabilisticActorPolicy
 from .optim import AdamOptimizerFactory, LRSchedulerFactoryLinear, OptimizerFactory, RMSpropOptimizerFactory
 
 __all__ = [
     "Algorithm", "OffPolicyAlgorithm", "OnPolicyAlgorithm", "Policy", "TrainingStats",
     "UnsupportedModelError", "A2CTrainingStats", "ActorCriticOnPolicyAlgorithm", "PPO",
-    "ProbabilisticActorPolicy", "AdamOptimizerFactory", "LRSchedulerFactoryLinear", "OptimizerFactory",
+    "ProbabilisticActorPolicy", "DiscreteActorPolicy", "AdamOptimizerFactory", "LRSchedulerFactoryLinear", "OptimizerFactory",
     "RMSpropOptimizerFactory",
 ]

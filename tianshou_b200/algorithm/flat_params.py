@@ -13,9 +13,9 @@ from typing import Any
 
 import torch
 from torch import nn
-from torch.distributions import Independent, Normal
+from torch.distributions import Categorical, Independent, Normal
 
-from .._cabi import ActorCriticDesc
+from .._cabi import AC_CATEGORICAL, AC_RELU, ActorCriticDesc
 
 
 class UnsupportedModelError(NotImplementedError):
@@ -30,8 +30,8 @@ def _single_linear(mlp: Any, what: str) -> nn.Linear:
     return mods[0]
 
 
-def _trunk(net: Any, what: str) -> tuple[nn.Linear, nn.Linear]:
-    """Net(obs -> 64 -> 64, Tanh) -> its two Linear layers."""
+def _trunk(net: Any, what: str) -> tuple[nn.Linear, nn.Linear, bool]:
+    """Net(obs -> 64 -> 64, Tanh | ReLU) -> its two Linear layers and whether the activation is ReLU."""
     mlp = getattr(net, "model", None)
     seq = getattr(mlp, "model", None)
     if seq is None:
@@ -39,24 +39,40 @@ def _trunk(net: Any, what: str) -> tuple[nn.Linear, nn.Linear]:
     mods = list(seq)
     lin = [m for m in mods if isinstance(m, nn.Linear)]
     act = [m for m in mods if not isinstance(m, nn.Linear)]
-    if len(lin) != 2 or len(mods) != 4 or not all(isinstance(a, nn.Tanh) for a in act):
+    tanh = all(isinstance(a, nn.Tanh) for a in act)
+    relu = all(type(a) is nn.ReLU for a in act)
+    if len(lin) != 2 or len(mods) != 4 or not (tanh or relu):
         raise UnsupportedModelError(
-            f"{what}: fused kernels support exactly Linear-Tanh-Linear-Tanh trunks, got {mods}")
+            f"{what}: fused kernels support exactly Linear-Act-Linear-Act trunks with Act = Tanh or ReLU, got {mods}")
     if getattr(net, "softmax", False):
         raise UnsupportedModelError(f"{what}: softmax trunk output unsupported")
-    return lin[0], lin[1]
+    return lin[0], lin[1], relu
 
 
 def describe_actor_critic(actor: Any, critic: Any) -> tuple[ActorCriticDesc, list[nn.Parameter]]:
-    """Validate the module structure and return (desc, parameters in flat-buffer order)."""
-    if getattr(actor, "_c_sigma", False) or not hasattr(actor, "sigma_param"):
-        raise UnsupportedModelError("actor: conditioned sigma unsupported (need state-independent sigma_param)")
-    if not getattr(actor, "_unbounded", False):
-        raise UnsupportedModelError("actor: only unbounded=True (mu without tanh) is supported")
-    a1, a2 = _trunk(actor.preprocess, "actor")
-    a3 = _single_linear(actor.mu, "actor.mu")
-    c1, c2 = _trunk(critic.preprocess, "critic")
+    """Validate the module structure and return (desc, parameters in flat-buffer order).
+
+    Two families: the MuJoCo one (ContinuousActorProbabilistic + ContinuousCritic, separate trunks, Gaussian head)
+    and the reference's discrete PPO test net (DiscreteActor(softmax_output=True) + DiscreteCritic, optionally on ONE
+    shared preprocess Net; test/discrete/test_ppo_discrete.py:90-100).  A shared trunk appears once in the flat
+    buffer and both networks' descriptor offsets alias it."""
+    discrete = hasattr(actor, "softmax_output")
+    if discrete:
+        if not actor.softmax_output:
+            raise UnsupportedModelError("actor: DiscreteActor needs softmax_output=True (Categorical over probabilities)")
+        head = _single_linear(actor.last, "actor.last")
+    else:
+        if getattr(actor, "_c_sigma", False) or not hasattr(actor, "sigma_param"):
+            raise UnsupportedModelError("actor: conditioned sigma unsupported (need state-independent sigma_param)")
+        if not getattr(actor, "_unbounded", False):
+            raise UnsupportedModelError("actor: only unbounded=True (mu without tanh) is supported")
+        head = _single_linear(actor.mu, "actor.mu")
+    a1, a2, a_relu = _trunk(actor.preprocess, "actor")
+    a3 = head
+    c1, c2, c_relu = _trunk(critic.preprocess, "critic")
     c3 = _single_linear(critic.last, "critic.last")
+    if a_relu != c_relu:
+        raise UnsupportedModelError("actor and critic trunks must use the same activation")
     if getattr(critic, "apply_preprocess_net_to_obs_only", False):
         raise UnsupportedModelError("critic: apply_preprocess_net_to_obs_only unsupported")
     H, obs = a1.out_features, a1.in_features
@@ -71,17 +87,38 @@ def describe_actor_critic(actor: Any, critic: Any) -> tuple[ActorCriticDesc, lis
     for lin in (a1, a2, a3, c1, c2, c3):
         if lin.bias is None:
             raise UnsupportedModelError("Linear layers need a bias")
-    params = [a1.weight, a1.bias, a2.weight, a2.bias, a3.weight, a3.bias, actor.sigma_param,
-              c1.weight, c1.bias, c2.weight, c2.bias, c3.weight, c3.bias]
+    shared = a1 is c1 and a2 is c2
+    if not shared and (a1 is c1 or a2 is c2):
+        raise UnsupportedModelError("partially shared trunks are unsupported")
+    named = [("a_w1", a1.weight), ("a_b1", a1.bias), ("a_w2", a2.weight), ("a_b2", a2.bias), ("a_w3", a3.weight),
+             ("a_b3", a3.bias)]
+    if not discrete:
+        named.append(("a_logstd", actor.sigma_param))
+    if not shared:
+        named += [("c_w1", c1.weight), ("c_b1", c1.bias), ("c_w2", c2.weight), ("c_b2", c2.bias)]
+    named += [("c_w3", c3.weight), ("c_b3", c3.bias)]
     d = ActorCriticDesc()
     d.obs_dim, d.act_dim, d.hidden = obs, act, H
+    d.flags = (AC_RELU if a_relu else 0) | (AC_CATEGORICAL if discrete else 0)
+    d.a_logstd = -1
     off = 0
-    for name, p in zip(["a_w1", "a_b1", "a_w2", "a_b2", "a_w3", "a_b3", "a_logstd",
-                        "c_w1", "c_b1", "c_w2", "c_b2", "c_w3", "c_b3"], params, strict=True):
+    for name, p in named:
         setattr(d, name, off)
         off += p.numel()
+    if shared:
+        d.c_w1, d.c_b1, d.c_w2, d.c_b2 = d.a_w1, d.a_b1, d.a_w2, d.a_b2
     d.n_params = off
-    return d, params
+    return d, [p for _, p in named]
+
+
+def check_categorical_dist_fn(dist_fn: Any, act_dim: int, device: torch.device) -> None:
+    """The categorical kernels hard-wire Categorical(probs = actor output) (test_ppo_discrete.py:108)."""
+    probs = torch.full((2, act_dim), 1.0 / act_dim, device=device)
+    probs[0, 0] += 0.25 / act_dim
+    probs[0, -1] -= 0.25 / act_dim
+    d = dist_fn(probs)
+    if not isinstance(d, Categorical) or not torch.allclose(d.probs, probs, atol=1e-6):
+        raise UnsupportedModelError(f"dist_fn must build Categorical(probs=actor output); got {d}")
 
 
 def check_gaussian_dist_fn(dist_fn: Any, act_dim: int, device: torch.device) -> None:

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from ... import ops
-from ..._cabi import GRAD_EXTRA, STATS_STRIDE, PPOHParams, to_device
+from ..._cabi import AC_CATEGORICAL, GRAD_EXTRA, STATS_STRIDE, PPOHParams, to_device
 from ...data import Batch, ReplayBuffer, SequenceSummaryStats
 from ...utils import RunningMeanStd
 from ...utils.net.common import ActorCritic
@@ -31,6 +31,7 @@ from ..flat_params import (
     FlatParams,
     UnsupportedModelError,
     adam_hyperparams,
+    check_categorical_dist_fn,
     check_gaussian_dist_fn,
     describe_actor_critic,
 )
@@ -75,7 +76,10 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         if dev.type != "cuda":
             raise UnsupportedModelError(
                 f"actor/critic live on {dev}; tianshou_b200 has no CPU path -- move them to a CUDA device first")
-        check_gaussian_dist_fn(self.policy.dist_fn, self._desc.act_dim, dev)
+        if self._desc.flags & AC_CATEGORICAL:
+            check_categorical_dist_fn(self.policy.dist_fn, self._desc.act_dim, dev)
+        else:
+            check_gaussian_dist_fn(self.policy.dist_fn, self._desc.act_dim, dev)
         self._flat = FlatParams(plist, dev, GRAD_EXTRA)
         # scratch for the pre-split (bf16x3) weight image of the tensor-core update kernel; None -> the
         # kernels gather + split the weights themselves (networks the tensor-core path does not cover)

@@ -45,3 +45,17 @@ class ProbabilisticActorPolicy(Policy):
         else:
             act = dist.sample()
         return Batch(logits=dist_input, act=act, state=hidden, dist=dist)
+
+
+class DiscreteActorPolicy(ProbabilisticActorPolicy):
+    """Categorical policy over a Discrete action space (reinforce.py:195-243): no action scaling / bounding."""
+
+    def __init__(self, *, actor: torch.nn.Module, dist_fn: TDistFn | None = None, deterministic_eval: bool = False,
+                 action_space: Any, observation_space: Any | None = None) -> None:
+        if not (type(action_space).__name__ == "Discrete" or hasattr(action_space, "n")):
+            raise ValueError(f"Action space must be an instance of Discrete; got {action_space}")
+        if dist_fn is None:
+            from ...utils.net.discrete import dist_fn_categorical_from_logits
+            dist_fn = dist_fn_categorical_from_logits
+        super().__init__(actor=actor, dist_fn=dist_fn, deterministic_eval=deterministic_eval, action_space=action_space,
+                         observation_space=observation_space, action_scaling=False, action_bound_method=None)

@@ -127,11 +127,13 @@ __device__ void load_rows(float* tile, int ld, int kpad, const float* __restrict
 
 // ---- 128 x 64 dense layer: OUT = epi(b + IN[128 x K] * Wk[K x 64]) ---------------------------
 // Thread (rg = tid>>4, cg = tid&15) owns rows {rg + 16 j, j<8} and columns {4 cg .. 4 cg + 3}.
-// EPI 0: tanh -> OUT;  EPI 1: acc * (1 - OUT^2) -> OUT (in-place derivative form, bias unused)
+// EPI 0: act(.) -> OUT;  EPI 1: acc * act'(OUT) -> OUT (in-place derivative form, bias unused).
+// relu: activation is max(x, 0) instead of tanh (the reference's Net default, common.py MLP); its derivative in
+// terms of the stored output h is (h > 0), exactly torch's (z > 0).
 template <int EPI>
 __device__ __forceinline__ void dense_128x64(const float* __restrict__ IN, int ldin, int K,
                                              const float* __restrict__ Wk,
-                                             const float* __restrict__ bias, float* OUT, int ldout) {
+                                             const float* __restrict__ bias, float* OUT, int ldout, bool relu) {
     const int tid = threadIdx.x;
     const int rg = tid >> 4, cg = tid & 15;
     float acc[8][4];
@@ -162,21 +164,24 @@ __device__ __forceinline__ void dense_128x64(const float* __restrict__ IN, int l
         float* o = OUT + (rg + 16 * j) * ldout + 4 * cg;
         float4 r;
         if (EPI == 0) {
-            r = make_float4(tanhf(acc[j][0]), tanhf(acc[j][1]), tanhf(acc[j][2]), tanhf(acc[j][3]));
+            r = relu ? make_float4(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f), fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f))
+                     : make_float4(tanhf(acc[j][0]), tanhf(acc[j][1]), tanhf(acc[j][2]), tanhf(acc[j][3]));
         } else {
             const float4 h = *reinterpret_cast<const float4*>(o);
-            r = make_float4(acc[j][0] * (1.0f - h.x * h.x), acc[j][1] * (1.0f - h.y * h.y),
-                            acc[j][2] * (1.0f - h.z * h.z), acc[j][3] * (1.0f - h.w * h.w));
+            r = relu ? make_float4(h.x > 0.f ? acc[j][0] : 0.f, h.y > 0.f ? acc[j][1] : 0.f,
+                                   h.z > 0.f ? acc[j][2] : 0.f, h.w > 0.f ? acc[j][3] : 0.f)
+                     : make_float4(acc[j][0] * (1.0f - h.x * h.x), acc[j][1] * (1.0f - h.y * h.y),
+                                   acc[j][2] * (1.0f - h.z * h.z), acc[j][3] * (1.0f - h.w * h.w));
         }
         *reinterpret_cast<float4*>(o) = r;
     }
 }
 
 // trunk forward: X -> H1 -> H2 (ends with a barrier)
-__device__ void trunk_forward(float* sm, const Layout& L, const NetOff& n) {
-    dense_128x64<0>(sm + L.X, L.LDX, L.KX, sm + n.w1t, sm + n.b1, sm + L.H1, LDH);
+__device__ void trunk_forward(float* sm, const Layout& L, const NetOff& n, bool relu) {
+    dense_128x64<0>(sm + L.X, L.LDX, L.KX, sm + n.w1t, sm + n.b1, sm + L.H1, LDH, relu);
     __syncthreads();
-    dense_128x64<0>(sm + L.H1, LDH, H, sm + n.w2t, sm + n.b2, sm + L.H2, LDH);
+    dense_128x64<0>(sm + L.H1, LDH, H, sm + n.w2t, sm + n.b2, sm + L.H2, LDH, relu);
     __syncthreads();
 }
 
@@ -210,6 +215,45 @@ __device__ __forceinline__ float normal_logp_term(float x, float mu, float sigma
     return -(diff * diff) / (2.0f * var) - logf(sigma) - 0.9189385332046727f;
 }
 
+// Categorical head exactly as the reference builds it (DiscreteActor(softmax_output=True) -> torch.distributions.
+// Categorical(probs), utils/net/discrete.py:69-92, reinforce.py:167-192): p = softmax(z); Categorical renormalises
+// (pn = p / sum p) and takes logits = log(clamp(pn, eps, 1 - eps)); log_prob gathers, entropy = -sum pn * logits.
+// fwd: returns log_prob(action) and the row entropy; keeps p, pn, lg for the backward.
+struct CatRow { float p[kMaxAct], pn[kMaxAct], lg[kMaxAct]; float s2; };
+__device__ __forceinline__ void categorical_forward(const float* z, int A, int action, CatRow& c, float& logp, float& ent) {
+    constexpr float eps = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
+    float m = z[0];
+    for (int a = 1; a < A; ++a) m = fmaxf(m, z[a]);
+    float s = 0.0f;
+    for (int a = 0; a < A; ++a) { c.p[a] = expf(z[a] - m); s += c.p[a]; }
+    float s2 = 0.0f;
+    for (int a = 0; a < A; ++a) { c.p[a] = c.p[a] / s; s2 += c.p[a]; }
+    c.s2 = s2;
+    ent = 0.0f;
+    for (int a = 0; a < A; ++a) {
+        c.pn[a] = c.p[a] / s2;
+        c.lg[a] = logf(fminf(fmaxf(c.pn[a], eps), 1.0f - eps));
+        ent -= c.pn[a] * c.lg[a];
+    }
+    logp = (action >= 0 && action < A) ? c.lg[action] : 0.0f;
+}
+// bwd: dz[a] = d loss / d logit a given gl = d loss / d log_prob and ge = d loss / d entropy (autograd's chain:
+// gather + entropy -> log o clamp -> renormalisation -> softmax)
+__device__ __forceinline__ void categorical_backward(const CatRow& c, int A, int action, float gl, float ge, float* dz) {
+    constexpr float eps = 1.1920928955078125e-07f;
+    float dpn[kMaxAct];
+    float dot = 0.0f;
+    for (int a = 0; a < A; ++a) {
+        const float dlg = (a == action ? gl : 0.0f) - ge * c.pn[a];
+        const bool pass = c.pn[a] >= eps && c.pn[a] <= 1.0f - eps;        // clamp backward
+        dpn[a] = -ge * c.lg[a] + (pass ? dlg / c.pn[a] : 0.0f);
+        dot += dpn[a] * c.pn[a];
+    }
+    float dot2 = 0.0f;
+    for (int a = 0; a < A; ++a) { dpn[a] = (dpn[a] - dot) / c.s2; dot2 += dpn[a] * c.p[a]; }   // now d/dp
+    for (int a = 0; a < A; ++a) dz[a] = c.p[a] * (dpn[a] - dot2);
+}
+
 // ---- kernels --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) critic_forward_kernel(
     const float* __restrict__ params, const ts_actor_critic_desc d, const float* __restrict__ obs0,
@@ -226,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) critic_forward_kernel(
         __syncthreads();
         load_rows(sm + L.X, L.LDX, L.KX, second ? obs1 : obs0, d.obs_dim, nullptr, row0, nrows);
         __syncthreads();
-        trunk_forward(sm, L, L.critic);
+        trunk_forward(sm, L, L.critic, (d.flags & TS_AC_RELU) != 0);
         if (threadIdx.x < nrows)
             (second ? out1 : out0)[row0 + threadIdx.x] = head_dot(sm, L, L.critic, threadIdx.x, 0);
     }
@@ -238,23 +282,34 @@ __global__ void __launch_bounds__(kThreads, 1) actor_logp_kernel(
     extern __shared__ __align__(16) float sm[];
     const Layout L = make_layout(d.obs_dim, d.act_dim, 1);
     const int A = d.act_dim;
-    stage_net(sm, L.actor, params, actor_global(d), d.obs_dim, L.KX, A, false, true);
+    const bool categorical = (d.flags & TS_AC_CATEGORICAL) != 0, relu = (d.flags & TS_AC_RELU) != 0;
+    const int act_w = categorical ? 1 : A;     // discrete actions are ONE index per row (stored as float)
+    stage_net(sm, L.actor, params, actor_global(d), d.obs_dim, L.KX, A, false, !categorical);
     const int64_t tiles = (n + kRows - 1) / kRows;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int64_t row0 = t * kRows;
         const int nrows = (int)tsb::imin((int64_t)kRows, n - row0);
         __syncthreads();
         load_rows(sm + L.X, L.LDX, L.KX, obs, d.obs_dim, nullptr, row0, nrows);
-        load_rows(sm + L.ACT, kMaxAct, A, act, A, nullptr, row0, nrows);
+        load_rows(sm + L.ACT, kMaxAct, act_w, act, act_w, nullptr, row0, nrows);
         __syncthreads();
-        trunk_forward(sm, L, L.actor);
+        trunk_forward(sm, L, L.actor, relu);
         // mu -> DOUT-less: reuse X tile region? keep it simple: each (r,a) pair writes mu to H1
         for (int o = threadIdx.x; o < kRows * A; o += kThreads) {
             const int r = o / A, a = o - r * A;
             sm[L.H1 + r * LDH + a] = head_dot(sm, L, L.actor, r, a);
         }
         __syncthreads();
-        if (threadIdx.x < nrows) {
+        if (threadIdx.x < nrows && categorical) {
+            const int r = threadIdx.x;
+            float z[kMaxAct];
+            for (int a = 0; a < A; ++a) z[a] = sm[L.H1 + r * LDH + a];
+            CatRow c;
+            float lp, ent;
+            categorical_forward(z, A, (int)sm[L.ACT + r * kMaxAct], c, lp, ent);
+            if (mu_out) for (int a = 0; a < A; ++a) mu_out[(row0 + r) * A + a] = c.p[a];   // the actor's output: probabilities
+            logp_out[row0 + r] = lp;
+        } else if (threadIdx.x < nrows) {
             const int r = threadIdx.x;
             float lp = 0.0f;
             for (int a = 0; a < A; ++a) {
@@ -286,7 +341,7 @@ __device__ void head_backward(const float* sm, const Layout& L, int out_dim, flo
     }
 }
 // H2 <- (DOUT * W3) * (1 - H2^2)     (dz2, in place)
-__device__ void head_input_grad(float* sm, const Layout& L, const NetOff& n, int out_dim) {
+__device__ void head_input_grad(float* sm, const Layout& L, const NetOff& n, int out_dim, bool relu) {
     const int tid = threadIdx.x, rg = tid >> 4, cg = tid & 15;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -300,8 +355,10 @@ __device__ void head_input_grad(float* sm, const Layout& L, const NetOff& n, int
         }
         float* hp = sm + L.H2 + r * LDH + 4 * cg;
         const float4 h = *reinterpret_cast<const float4*>(hp);
-        *reinterpret_cast<float4*>(hp) = make_float4(acc.x * (1.f - h.x * h.x), acc.y * (1.f - h.y * h.y),
-                                                     acc.z * (1.f - h.z * h.z), acc.w * (1.f - h.w * h.w));
+        *reinterpret_cast<float4*>(hp) =
+            relu ? make_float4(h.x > 0.f ? acc.x : 0.f, h.y > 0.f ? acc.y : 0.f, h.z > 0.f ? acc.z : 0.f, h.w > 0.f ? acc.w : 0.f)
+                 : make_float4(acc.x * (1.f - h.x * h.x), acc.y * (1.f - h.y * h.y),
+                               acc.z * (1.f - h.z * h.z), acc.w * (1.f - h.w * h.w));
     }
 }
 // gW[o][i] += sum_r DZ[r][o] * IN[r][i]  (64 x 64), gb[o] += sum_r DZ[r][o]
@@ -358,14 +415,14 @@ __device__ void weight_grad_first(const float* __restrict__ DZ, const float* __r
 
 // backward through one trunk given DOUT (head gradient) and H1/H2/X of the tile
 __device__ void trunk_backward(float* sm, const Layout& L, const NetOff& n, const NetGlobal& g,
-                               int out_dim, int obs_dim, float* __restrict__ grad) {
+                               int out_dim, int obs_dim, float* __restrict__ grad, bool relu) {
     head_backward(sm, L, out_dim, grad, g.w3, g.b3);
     __syncthreads();
-    head_input_grad(sm, L, n, out_dim);                              // H2 := dz2
+    head_input_grad(sm, L, n, out_dim, relu);                        // H2 := dz2
     __syncthreads();
     weight_grad_64x64(sm + L.H2, sm + L.H1, grad, g.w2, g.b2);       // reads H1, dz2
     __syncthreads();
-    dense_128x64<1>(sm + L.H2, LDH, H, sm + n.w2, nullptr, sm + L.H1, LDH);  // H1 := dz1
+    dense_128x64<1>(sm + L.H2, LDH, H, sm + n.w2, nullptr, sm + L.H1, LDH, relu);  // H1 := dz1
     __syncthreads();
     weight_grad_first(sm + L.H1, sm + L.X, L.LDX, obs_dim, grad, g.w1, g.b1);
     __syncthreads();
@@ -397,7 +454,11 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
     float* __restrict__ grad = partials + (size_t)blockIdx.x * (size_t)(d.n_params + TS_PPO_GRAD_EXTRA);
     for (int64_t i = tid; i < d.n_params + TS_PPO_GRAD_EXTRA; i += kThreads) grad[i] = 0.0f;
     const NetGlobal ga = actor_global(d), gc = critic_global(d);
-    stage_net(sm, L.actor, params, ga, d.obs_dim, L.KX, A, true, true);
+    const bool categorical = (d.flags & TS_AC_CATEGORICAL) != 0, relu = (d.flags & TS_AC_RELU) != 0;
+    const int act_w = categorical ? 1 : A;
+    // A shared trunk (DiscreteActor / DiscreteCritic on one preprocess net) is expressed by ALIASED offsets
+    // (c_w1 == a_w1, ...): both backward passes add into the same gradient slots of this CTA's row.
+    stage_net(sm, L.actor, params, ga, d.obs_dim, L.KX, A, true, !categorical);
     stage_net(sm, L.critic, params, gc, d.obs_dim, L.KX, 1, true, false);
     const float inv_b = 1.0f / (float)global_rows;
     const float eps_clip = (float)hp.eps_clip, lo_c = (float)(1.0 - hp.eps_clip), hi_c = (float)(1.0 + hp.eps_clip);
@@ -413,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
         const int nrows = (int)tsb::imin((int64_t)kRows, hi - pos0);
         __syncthreads();
         load_rows(sm + L.X, L.LDX, L.KX, obs, d.obs_dim, perm, pos0, nrows);
-        load_rows(sm + L.ACT, kMaxAct, A, act, A, perm, pos0, nrows);
+        load_rows(sm + L.ACT, kMaxAct, act_w, act, act_w, perm, pos0, nrows);
         if (tid < kRows) {
             float a_ = 0.f, r_ = 0.f, l_ = 0.f, v_ = 0.f;
             if (tid < nrows) {
@@ -425,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
         __syncthreads();
 
         // ================= critic: forward, value loss, backward ===========================
-        trunk_forward(sm, L, L.critic);
+        trunk_forward(sm, L, L.critic, relu);
         float vf_row = 0.0f;
         if (tid < kRows) {
             float dv = 0.0f;
@@ -454,17 +515,54 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
             sm[L.DOUT + tid * LDO] = dv;
         }
         __syncthreads();
-        trunk_backward(sm, L, L.critic, gc, 1, d.obs_dim, grad);
+        trunk_backward(sm, L, L.critic, gc, 1, d.obs_dim, grad, relu);
 
         // ================= actor: forward, clipped surrogate, backward =======================
-        trunk_forward(sm, L, L.actor);
-        for (int o = tid; o < kRows * A; o += kThreads) {   // mu into DOUT[r][a] (overwritten below)
+        trunk_forward(sm, L, L.actor, relu);
+        for (int o = tid; o < kRows * A; o += kThreads) {   // mu / logits into DOUT[r][a] (overwritten below)
             const int r = o / A, a = o - r * A;
             sm[L.DOUT + r * LDO + a] = head_dot(sm, L, L.actor, r, a);
         }
         __syncthreads();
-        float clip_row = 0.0f;
-        if (tid < kRows) {
+        float clip_row = 0.0f, ent_row = 0.0f;
+        // PPO surrogate of one row: objective value and d loss / d log_prob           (ppo.py:184-196)
+        auto surrogate = [&](int r, float lp, float& obj) -> float {
+            float Adv = rowv[r];
+            if (hp.advantage_normalization) Adv = (Adv - adv_mean) / (adv_std + adv_eps);
+            const float ratio = expf(lp - rowv[2 * kRows + r]);
+            const float rc = fminf(fmaxf(ratio, lo_c), hi_c);
+            const bool in_range = (ratio >= lo_c) && (ratio <= hi_c);
+            const float surr1 = ratio * Adv, surr2 = rc * Adv;
+            // d min(surr1, surr2) / d ratio with torch's tie rule (half to each branch)
+            float g_ratio;
+            if (surr1 < surr2) g_ratio = Adv;
+            else if (surr1 > surr2) g_ratio = in_range ? Adv : 0.0f;
+            else g_ratio = in_range ? Adv : 0.5f * Adv;
+            const float clip1 = fminf(surr1, surr2);
+            obj = clip1;
+            if (dual_clip > 0.0f && Adv < 0.0f) {   // ppo.py:191-194
+                const float c2 = dual_clip * Adv;
+                obj = fmaxf(clip1, c2);
+                if (clip1 < c2) g_ratio = 0.0f; else if (clip1 == c2) g_ratio *= 0.5f;
+            }
+            return -inv_b * g_ratio * ratio;
+        };
+        if (tid < kRows && categorical) {
+            const int r = tid;
+            float z[kMaxAct], dz[kMaxAct];
+            for (int a = 0; a < A; ++a) z[a] = sm[L.DOUT + r * LDO + a];
+            const int action = (int)sm[L.ACT + r * kMaxAct];
+            CatRow c;
+            float lp, ent;
+            categorical_forward(z, A, action, c, lp, ent);
+            for (int a = 0; a < A; ++a) dz[a] = 0.0f;
+            if (r < nrows) {
+                const float gl = surrogate(r, lp, clip_row);
+                ent_row = ent;
+                categorical_backward(c, A, action, gl, -ent_coef * inv_b, dz);
+            }
+            for (int a = 0; a < A; ++a) sm[L.DOUT + r * LDO + a] = dz[a];
+        } else if (tid < kRows) {
             const int r = tid;
             float gl = 0.0f;     // d loss / d logp for this row
             float lp = 0.0f;
@@ -477,28 +575,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
                     lp += normal_logp_term(sm[L.ACT + r * kMaxAct + a], mu[a], sig[a]);
                 }
             }
-            if (r < nrows) {
-                float Adv = rowv[r];
-                if (hp.advantage_normalization) Adv = (Adv - adv_mean) / (adv_std + adv_eps);
-                const float ratio = expf(lp - rowv[2 * kRows + r]);
-                const float rc = fminf(fmaxf(ratio, lo_c), hi_c);
-                const bool in_range = (ratio >= lo_c) && (ratio <= hi_c);
-                const float surr1 = ratio * Adv, surr2 = rc * Adv;
-                // d min(surr1, surr2) / d ratio with torch's tie rule (half to each branch)
-                float g_ratio;
-                if (surr1 < surr2) g_ratio = Adv;
-                else if (surr1 > surr2) g_ratio = in_range ? Adv : 0.0f;
-                else g_ratio = in_range ? Adv : 0.5f * Adv;
-                float clip1 = fminf(surr1, surr2);
-                float obj = clip1;
-                if (dual_clip > 0.0f && Adv < 0.0f) {   // ppo.py:191-194
-                    const float c2 = dual_clip * Adv;
-                    obj = fmaxf(clip1, c2);
-                    if (clip1 < c2) g_ratio = 0.0f; else if (clip1 == c2) g_ratio *= 0.5f;
-                }
-                clip_row = obj;
-                gl = -inv_b * g_ratio * ratio;
-            }
+            if (r < nrows) gl = surrogate(r, lp, clip_row);
 #pragma unroll
             for (int a = 0; a < kMaxAct; ++a) {
                 if (a < A) {
@@ -511,24 +588,25 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
         }
         __syncthreads();
         // logstd gradient: column sums of DOUT[:, 16..16+A) plus the entropy term
-        if (tid < A) {
+        if (tid < A && !categorical) {
             float s = 0.0f;
             for (int r = 0; r < kRows; ++r) s += sm[L.DOUT + r * LDO + 16 + tid];
             s += -ent_coef * inv_b * (float)nrows;   // d(-ent_coef * mean(entropy))/d logstd
             atomicAdd(grad + d.a_logstd + tid, s);
         }
-        trunk_backward(sm, L, L.actor, ga, A, d.obs_dim, grad);
+        trunk_backward(sm, L, L.actor, ga, A, d.obs_dim, grad, relu);
 
         // ================= loss sums ==========================================================
         const float s_clip = block_sum_128(tid < kRows ? clip_row : 0.0f, sm + L.RED);
         const float s_vf = block_sum_128(tid < kRows ? vf_row : 0.0f, sm + L.RED);
+        const float s_ent = block_sum_128(tid < kRows ? ent_row : 0.0f, sm + L.RED);      // categorical: per-row entropies
         if (tid == 0) {
             float ent = 0.0f;   // Normal entropy: 0.5 + 0.5 log(2 pi) + log(sigma), summed over dims
-            for (int a = 0; a < A; ++a) ent += 1.4189385332046727f + logf(expf(sm[L.actor.ls + a]));
+            if (!categorical) for (int a = 0; a < A; ++a) ent += 1.4189385332046727f + logf(expf(sm[L.actor.ls + a]));
             float* ex = grad + d.n_params;
             atomicAdd(ex + 0, s_clip);
             atomicAdd(ex + 1, s_vf);
-            atomicAdd(ex + 2, ent * (float)nrows);
+            atomicAdd(ex + 2, categorical ? s_ent : ent * (float)nrows);
             atomicAdd(ex + 3, (float)nrows);
         }
     }
@@ -783,6 +861,8 @@ int check_desc(const ts_actor_critic_desc* d, const char* fn) {
     TS_REQUIRE(d->hidden == H, "%s: hidden width %d unsupported (only %d)", fn, d->hidden, H);
     TS_REQUIRE(d->obs_dim >= 1 && d->obs_dim <= kMaxObs, "%s: obs_dim %d out of [1,%d]", fn, d->obs_dim, kMaxObs);
     TS_REQUIRE(d->act_dim >= 1 && d->act_dim <= kMaxAct, "%s: act_dim %d out of [1,%d]", fn, d->act_dim, kMaxAct);
+    TS_REQUIRE((d->flags & ~(TS_AC_RELU | TS_AC_CATEGORICAL)) == 0, "%s: unknown desc flags 0x%x", fn, d->flags);
+    TS_REQUIRE((d->flags & TS_AC_CATEGORICAL) || d->a_logstd >= 0, "%s: Gaussian head needs a_logstd", fn);
     return 0;
 }
 

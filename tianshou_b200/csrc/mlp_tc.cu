@@ -1164,7 +1164,10 @@ extern "C" int ts_tc_timeline(int32_t enable, uint64_t* out32 /* host, nullable 
 
 namespace tsb {
 bool tc_supported(const ts_actor_critic_desc& d) {
-    return d.hidden == H && d.obs_dim >= 1 && d.obs_dim <= 32 && d.act_dim >= 1 && d.act_dim <= kMaxAct;
+    // tanh trunks, Gaussian head, separate actor / critic parameters (a shared trunk = aliased offsets would break
+    // the store-not-add gradient write-out); everything else runs the fp32 SIMT kernels
+    return d.hidden == H && d.obs_dim >= 1 && d.obs_dim <= 32 && d.act_dim >= 1 && d.act_dim <= kMaxAct && d.flags == 0 &&
+           d.a_w1 != d.c_w1 && d.a_logstd >= 0;
 }
 
 static int configure_ppo_smem(size_t smem) {
