@@ -976,12 +976,16 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
 
 
 // ---- forward-only kernels (value pass / log-prob pass), persistent over 128-row tiles -----------
-// Two tiles are in flight per CTA (slots 0 / 1: own X, H1 operands and D1, D2 accumulators): the MMAs of one
-// slot run on the tensor core while the 16 warps do the other slot's epilogues, and the next tiles' rows are
-// loaded from global memory one stage ahead of their conversion into operands.
+// TS mode: the activations (X, H1) are the A operand IN TENSOR MEMORY -- the staging / epilogue threads split
+// them to bf16x3 and tcgen05.st them to their own TMEM lane (lane = row), so an MMA reads only the 2 KB weight
+// operand from shared memory and runs at its 32-cycle math floor instead of being paced by 6 KB of operand reads
+// (ncu, SS mode: tensor pipe busy 76 % of the pass).  Two tiles are in flight per CTA (slots 0 / 1: own
+// accumulator and operand columns): the MMAs of one slot run while the 16 warps do the other slot's epilogues, and
+// the next tiles' rows are loaded from global memory one stage ahead of their conversion.
+// TMEM columns of a slot: D (64: layer-1, then layer-2 accumulator) | T (96: X pieces, then H1 pieces).
 struct SmemF {
     int KXP;
-    Mat X[2], H1[2], W1, W2;
+    Mat W1, W2;
     uint32_t w3f, b1, b2, b3, ls, part;
     uint32_t total;
 };
@@ -992,10 +996,6 @@ __host__ __device__ inline SmemF make_smem_f(int obs_dim, uint32_t sbase) {
     auto mat = [&](Mat& m, int rows, int cols) {
         m.base = sbase + o; m.part = mat_bytes(rows, cols); m.RS = (uint32_t)(cols / 8) * 128u; o += 3u * m.part;
     };
-    mat(s.X[0], kRows, s.KXP);
-    mat(s.X[1], kRows, s.KXP);
-    mat(s.H1[0], kRows, H);
-    mat(s.H1[1], kRows, H);
     mat(s.W1, H, s.KXP);
     mat(s.W2, H, H);
     s.w3f = o;  o += kMaxAct * H * 4;
@@ -1007,10 +1007,12 @@ __host__ __device__ inline SmemF make_smem_f(int obs_dim, uint32_t sbase) {
     s.total = o;
     return s;
 }
+constexpr uint32_t kSlotCols = 160, kSlotD = 0, kSlotT = 64;     // 2 slots -> 320 columns (512 allocated)
 
-// all threads: publish smem operands / retire TMEM reads, then warp 0 issues `f` and commits to `bar` (no wait)
+// all threads: publish smem / TMEM operands, retire TMEM reads, then warp 0 issues `f` and commits to `bar` (no wait)
 template <class F>
 __device__ __forceinline__ void mma_issue(uint64_t* bar, F&& f) {
+    umma::tmem_wait_st();
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
@@ -1027,6 +1029,15 @@ __device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t& phase) {
     phase ^= 1u;
     umma::fence_after_sync();
 }
+// 16 consecutive values of the calling thread's row -> bf16x3 -> 8 packed columns per piece of its TMEM lane
+__device__ __forceinline__ void store_row16_tmem(uint32_t t_lane, uint32_t col0, uint32_t part_cols, const float* v) {
+    uint32_t w0[8], w1[8], w2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split3_pair(v[2 * j], v[2 * j + 1], w0[j], w1[j], w2[j]);
+    umma::tmem_st8(t_lane + col0, w0);
+    umma::tmem_st8(t_lane + col0 + part_cols, w1);
+    umma::tmem_st8(t_lane + col0 + 2u * part_cols, w2);
+}
 
 // MODE 0: out0[r] = critic(in0[r]) and (if in1) out1[r] = critic(in1[r])      (a2c.py:123-126)
 // MODE 1: out0[r] = log N(in1[r] | mu(in0[r]), exp(logstd)), out1 = mu (nullable)   (ppo.py:157-161)
@@ -1038,19 +1049,20 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
     __shared__ uint32_t s_tmem;
     __shared__ __align__(8) uint64_t s_bar[2][2];      // [slot][layer]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cq = warp >> 2;
     const uint32_t sbase = umma::smem_u32(sm);
     uint8_t* sm0 = sm - sbase;
     const SmemF S = make_smem_f(d.obs_dim, sbase);
     const int out_dim = MODE == 0 ? 1 : d.act_dim;
     const NetG g = MODE == 0 ? NetG{d.c_w1, d.c_b1, d.c_w2, d.c_b2, d.c_w3, d.c_b3, -1}
                              : NetG{d.a_w1, d.a_b1, d.a_w2, d.a_b2, d.a_w3, d.a_b3, d.a_logstd};
-    if (warp == 0) umma::tmem_alloc(&s_tmem, 256);
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
     if (tid == 0) {
         umma::mbar_init(&s_bar[0][0], 1); umma::mbar_init(&s_bar[0][1], 1);
         umma::mbar_init(&s_bar[1][0], 1); umma::mbar_init(&s_bar[1][1], 1);
         umma::fence_mbar_init();
     }
-    // weights: W1, W2 as tensor-core operands; head weights / biases as fp32
+    // weights: W1, W2 as tensor-core B operands (shared memory); head weights / biases as fp32
     stage_chunks(sm0, S.W1, H, d.obs_dim, S.KXP, [&](int o) { return params + g.w1 + (int64_t)o * d.obs_dim; });
     stage_chunks(sm0, S.W2, H, H, H, [&](int o) { return params + g.w2 + (int64_t)o * H; });
     float* w3f = reinterpret_cast<float*>(sm + S.w3f);
@@ -1070,7 +1082,9 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
+    const uint32_t t_lane = tmem + ((32u * q) << 16);       // this thread's TMEM lane group
     uint32_t ph[2][2] = {{0u, 0u}, {0u, 0u}};
+    const uint32_t xcols = (uint32_t)S.KXP / 2u;            // packed columns of one X piece (8 or 16)
 
     const int64_t tiles_per = (n + kRows - 1) / kRows;
     const int64_t tiles = tiles_per * ((MODE == 0 && in1) ? 2 : 1);
@@ -1082,75 +1096,102 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
         nrows = (int)tsb::imin((int64_t)kRows, n - row0);
         src = (MODE == 0 && second) ? in1 : in0;
     };
-    // the tile's rows are contiguous in memory: coalesced read (x_load), bf16x3 conversion later (x_store)
-    auto x_load = [&](int64_t k, float (&xv)[8]) {
+    // X staging: thread (q, cq, lane) owns row 32 q + lane, columns [16 cq, 16 cq + 16) (warps with 16 cq >= KXP idle)
+    const bool x_owner = 16 * cq < S.KXP;
+    auto x_load = [&](int64_t k, float (&xv)[16]) {
+        if (!x_owner) return;
         const float* src; int64_t row0; int nrows; bool second;
         tile_src(tile_of(k), src, row0, nrows, second);
-        chunk_load(kRows, d.obs_dim, S.KXP, [&](int r) { return r < nrows ? src + (row0 + r) * d.obs_dim : (const float*)nullptr; }, xv);
+        const int r = 32 * q + lane;
+        const float* row = src + (row0 + r) * d.obs_dim;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = 16 * cq + j;
+            xv[j] = (r < nrows && c < d.obs_dim) ? __ldg(row + c) : 0.0f;
+        }
+    };
+    auto x_store = [&](int slot, const float (&xv)[16]) {
+        if (x_owner) store_row16_tmem(t_lane, kSlotCols * slot + kSlotT + 8u * cq, xcols, xv);
     };
     auto l1 = [&](int slot) {
-        mma_issue(&s_bar[slot][0], [&] { gemm_kx(tmem + 128u * slot + cD1, 128, H, S.X[slot], 0, S.W1, 0, S.KXP); });
+        mma_issue(&s_bar[slot][0], [&] {
+            const uint32_t dcol = tmem + kSlotCols * slot + kSlotD, acol = tmem + kSlotCols * slot + kSlotT;
+            const uint32_t idesc = umma::idesc_bf16(128, H, 0, 0);
+            if (S.KXP == 16) umma::gemm_bf16x3_ts_warp<1>(dcol, acol, xcols, S.W1.base, S.W1.part, 128u, S.W1.RS, 256u, idesc);
+            else umma::gemm_bf16x3_ts_warp<2>(dcol, acol, xcols, S.W1.base, S.W1.part, 128u, S.W1.RS, 256u, idesc);
+        });
     };
-    auto epi1_l2 = [&](int slot) {     // h1 = tanh(D1 + b1) -> H1[slot]; issue layer 2
+    auto epi1_l2 = [&](int slot) {     // h1 = tanh(D + b1) -> T (3 x 32 packed columns); issue layer 2 into D
         mma_wait(&s_bar[slot][0], ph[slot][0]);
-        float h1[kCols];
-        epi_tanh(sm0, S.H1[slot], tmem + 128u * slot, cD1, b1, h1);
-        mma_issue(&s_bar[slot][1], [&] { gemm<H / 16>(tmem + 128u * slot + cD2, 128, H, S.H1[slot], 0, S.W2, 0); });
+        {
+            const uint32_t c0 = (uint32_t)kCols * cq;
+            float h[kCols];
+            umma::tmem_ld16(t_lane + kSlotCols * slot + kSlotD + c0, h);
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) h[j] = tanh_mufu(h[j] + b1[c0 + j]);
+            store_row16_tmem(t_lane, kSlotCols * slot + kSlotT + 8u * cq, (uint32_t)H / 2u, h);
+        }
+        mma_issue(&s_bar[slot][1], [&] {
+            umma::gemm_bf16x3_ts_warp<H / 16>(tmem + kSlotCols * slot + kSlotD, tmem + kSlotCols * slot + kSlotT, (uint32_t)H / 2u,
+                                              S.W2.base, S.W2.part, 128u, S.W2.RS, 256u, umma::idesc_bf16(128, H, 0, 0));
+        });
     };
-    auto epi2 = [&](int slot, int64_t k) {   // h2 = tanh(D2 + b2) in registers; head = h2 . W3^T (K = 64 split over the four column groups)
+    auto epi2 = [&](int slot, int64_t k) {   // h2 = tanh(D + b2) in registers; head = h2 . W3^T (K = 64 split over the four column groups)
         const float* src; int64_t row0; int nrows; bool second;
         tile_src(tile_of(k), src, row0, nrows, second);
         mma_wait(&s_bar[slot][1], ph[slot][1]);
         {
-            const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
+            const uint32_t r = 32u * q + lane, c0 = (uint32_t)kCols * cq;
             float v[kCols];
-            umma::tmem_ld16(tmem + 128u * slot + ((32u * (warp & 3)) << 16) + cD2 + c0, v);
+            umma::tmem_ld16(t_lane + kSlotCols * slot + kSlotD + c0, v);
 #pragma unroll
             for (int j = 0; j < kCols; ++j) v[j] = tanh_mufu(v[j] + b2[c0 + j]);
             for (int a = 0; a < out_dim; ++a) {
                 float acc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < kCols; ++j) acc = fmaf(v[j], w3f[a * H + c0 + j], acc);
-                part[((warp >> 2) * kRows + r) * kMaxAct + a] = acc;
+                part[(cq * kMaxAct + a) * kRows + r] = acc;     // [column group][a][row]: rows on consecutive banks
             }
         }
+        umma::fence_before_sync();
         __syncthreads();
         if (tid < nrows) {
             const int r = tid;
             if (MODE == 0) {
-                (second ? out1 : out0)[row0 + r] = (part[r * kMaxAct] + part[(kRows + r) * kMaxAct]) +
-                                                   (part[(2 * kRows + r) * kMaxAct] + part[(3 * kRows + r) * kMaxAct]) + b3[0];
+                (second ? out1 : out0)[row0 + r] = (part[r] + part[kMaxAct * kRows + r]) +
+                                                   (part[2 * kMaxAct * kRows + r] + part[3 * kMaxAct * kRows + r]) + b3[0];
             } else {
                 float lp = 0.0f;
                 for (int a = 0; a < out_dim; ++a) {
-                    const float mu = (part[r * kMaxAct + a] + part[(kRows + r) * kMaxAct + a]) +
-                                     (part[(2 * kRows + r) * kMaxAct + a] + part[(3 * kRows + r) * kMaxAct + a]) + b3[a];
+                    const float* pa = part + a * kRows + r;
+                    const float mu = (pa[0] + pa[kMaxAct * kRows]) + (pa[2 * kMaxAct * kRows] + pa[3 * kMaxAct * kRows]) + b3[a];
                     lp += ppo::normal_logp_term(__ldg(in1 + (row0 + r) * out_dim + a), mu, ls[a]);
                     if (out1) out1[(row0 + r) * out_dim + a] = mu;
                 }
                 out0[row0 + r] = lp;
             }
         }
-        __syncthreads();     // `part` is free again
+        __syncthreads();     // `part` is free again; every thread has read this slot's D (layer 1 of the next tile may overwrite it)
     };
 
-    float xa[8], xb[8];
-    if (my_n > 0) { x_load(0, xa); chunk_store(sm0, S.X[0], kRows, S.KXP, xa); l1(0); }
-    if (my_n > 1) { x_load(1, xb); chunk_store(sm0, S.X[1], kRows, S.KXP, xb); l1(1); }
+    float xa[16], xb[16];
+    if (my_n > 0) { x_load(0, xa); x_store(0, xa); l1(0); }
+    if (my_n > 1) { x_load(1, xb); x_store(1, xb); l1(1); }
     for (int64_t k = 0; k < my_n; k += 2) {
         const bool hasB = k + 1 < my_n, nextA = k + 2 < my_n, nextB = k + 3 < my_n;
         if (nextA) x_load(k + 2, xa);              // global loads fly under the epilogues below
         epi1_l2(0);
         if (nextB) x_load(k + 3, xb);
         if (hasB) epi1_l2(1);                      // layer 2 of slot 0 runs on the tensor core meanwhile
-        if (nextA) { chunk_store(sm0, S.X[0], kRows, S.KXP, xa); l1(0); }     // X[0] / D1[0] are free: layer 1 of tile k was consumed
         epi2(0, k);
-        if (nextB) { chunk_store(sm0, S.X[1], kRows, S.KXP, xb); l1(1); }
+        // slot 0 is completely retired (its T columns were last read by layer 2, its D by the epilogue above)
+        if (nextA) { x_store(0, xa); l1(0); }
         if (hasB) epi2(1, k + 1);
+        if (nextB) { x_store(1, xb); l1(1); }
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 256);
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace

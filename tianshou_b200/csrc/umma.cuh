@@ -80,6 +80,21 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// TS mode: the A operand ([M = 128 lanes] x [K = 16 bf16 = 8 packed 32-bit columns], K-major only) comes from
+// tensor memory instead of shared memory -- an M128 x N64 x K16 MMA then reads 2 KB (B) instead of 6 KB from smem.
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 8 consecutive 32-bit columns of the calling thread's TMEM lane (thread t of warp w <-> lane 32 * (w % 4) + t)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
@@ -222,6 +237,38 @@ __device__ __forceinline__ void gemm_bf16x3_warp(uint32_t d_tmem, uint32_t a0, u
             if (A_PIECES == 3) { mma_bf16(d_tmem, A[1], B[0], idesc, first ? 0u : 1u); first = false; }
             if (B_PIECES == 3) { mma_bf16(d_tmem, A[0], B[1], idesc, first ? 0u : 1u); first = false; }
             mma_bf16(d_tmem, A[0], B[0], idesc, first ? 0u : 1u);
+        }
+    }
+    __syncwarp();
+}
+
+// Same six-product scheme with the A pieces in TMEM: piece p at columns a_tmem + p * a_part_cols, K step k at
+// + 8 k columns (2 bf16 per column).  WARP-LEVEL like gemm_bf16x3_warp.
+template <int KSTEPS>
+__device__ __forceinline__ void gemm_bf16x3_ts_warp(uint32_t d_tmem, uint32_t a_tmem, uint32_t a_part_cols, uint32_t b0,
+                                                    uint32_t b_part, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
+                                                    uint32_t idesc) {
+    const uint32_t bhi = desc_hi(b_sbo);
+    uint32_t blo[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) blo[p] = desc_lo(b0 + p * b_part, b_lbo);
+    const uint32_t bstep = b_step >> 4;
+    if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < KSTEPS; ++k) {
+            uint32_t A[3];
+            uint64_t B[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                A[p] = a_tmem + p * a_part_cols + 8u * k;
+                B[p] = desc_pack(blo[p] + k * bstep, bhi);
+            }
+            mma_bf16_ts(d_tmem, A[2], B[0], idesc, k == 0 ? 0u : 1u);
+            mma_bf16_ts(d_tmem, A[0], B[2], idesc, 1u);
+            mma_bf16_ts(d_tmem, A[1], B[1], idesc, 1u);
+            mma_bf16_ts(d_tmem, A[1], B[0], idesc, 1u);
+            mma_bf16_ts(d_tmem, A[0], B[1], idesc, 1u);
+            mma_bf16_ts(d_tmem, A[0], B[0], idesc, 1u);
         }
     }
     __syncwarp();

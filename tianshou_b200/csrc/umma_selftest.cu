@@ -51,17 +51,55 @@ __global__ void __launch_bounds__(kThreads, 1) umma_selftest_kernel(const float*
     };
     uint32_t aRS, aCS, aB, bRS, bCS, bB;
     uint8_t* a_base = smem;
+    const bool a_ts = (a_mn == 2);        // A operand in tensor memory (TS mode): bf16, M = 128, K-major
+    if (a_ts) a_mn = 0;
     place(a, M, a_mn, a_base, aRS, aCS, aB);
     uint8_t* b_base = a_base + (size_t)parts * aB;
     place(b, N, b_mn, b_base, bRS, bCS, bB);
-    if (warp == 0) umma::tmem_alloc(&s_tmem, 128);
+    if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
     if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::fence_mbar_init(); }
     umma::fence_async_smem();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    if (tid == 0) {
+    constexpr uint32_t kACol = 256;        // A pieces: columns 256 + p * 64 + (k / 2)
+    if (a_ts) {                            // thread = lane = row of A: split to bf16x3 and tcgen05.st 8 packed columns per K step
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t w[3][8];
+            for (int j = 0; j < 8; ++j) {
+                uint32_t pk[3] = {0u, 0u, 0u};
+                for (int h = 0; h < 2; ++h) {
+                    const float x = a[tid * K + k0 + 2 * j + h];
+                    const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+                    const float r1 = x - __bfloat162float(b0);
+                    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+                    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1 - __bfloat162float(b1));
+                    pk[0] |= (uint32_t)__bfloat16_as_ushort(b0) << (16 * h);
+                    pk[1] |= (uint32_t)__bfloat16_as_ushort(b1) << (16 * h);
+                    pk[2] |= (uint32_t)__bfloat16_as_ushort(b2) << (16 * h);
+                }
+                w[0][j] = pk[0]; w[1][j] = pk[1]; w[2][j] = pk[2];
+            }
+            for (int p = 0; p < 3; ++p)
+                umma::tmem_st8(tmem + ((uint32_t)(32 * warp) << 16) + kACol + 64u * p + (uint32_t)(k0 / 2), w[p]);
+        }
+        umma::tmem_wait_st();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        if (warp == 0) {
+            uint32_t blbo = bCS, bsbo = bRS, bstep = 2 * bCS;
+            if (b_mn) { bsbo = bCS; blbo = bRS; bstep = 2 * bRS; }
+            const uint32_t B0 = umma::smem_u32(b_base);
+            const uint32_t idesc = umma::idesc_bf16(M, N, 0, b_mn);
+            if (K == 16) umma::gemm_bf16x3_ts_warp<1>(tmem, tmem + kACol, 64u, B0, bB, blbo, bsbo, bstep, idesc);
+            else if (K == 32) umma::gemm_bf16x3_ts_warp<2>(tmem, tmem + kACol, 64u, B0, bB, blbo, bsbo, bstep, idesc);
+            else umma::gemm_bf16x3_ts_warp<4>(tmem, tmem + kACol, 64u, B0, bB, blbo, bsbo, bstep, idesc);
+            if (umma::elect_one()) umma::mma_commit(&s_bar);
+            __syncwarp();
+        }
+    } else if (tid == 0) {
         const int kper = dtype == 0 ? 8 : 16;
         auto strides = [&](int mn_major, uint32_t RS, uint32_t CS, uint32_t& lbo, uint32_t& sbo, uint32_t& step) {
             if (!mn_major) { lbo = CS; sbo = RS; step = 2 * CS; }        // K-major: 2 chunks of 16 B per MMA
@@ -90,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) umma_selftest_kernel(const float*
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 128);
+    if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -102,6 +140,7 @@ extern "C" int ts_umma_selftest(const float* a, const float* b, float* d, int32_
     const int kper = dtype == 0 ? 8 : 16;
     TS_REQUIRE(N % 8 == 0 && N >= 8 && N <= 128 && K % kper == 0 && K >= kper && K <= 128, "ts_umma_selftest: bad N/K");
     TS_REQUIRE(M == 64 || N % 16 == 0, "ts_umma_selftest: M=128 needs N % 16 == 0");
+    TS_REQUIRE(a_mn != 2 || (dtype == 1 && M == 128 && (K == 16 || K == 32 || K == 64)), "ts_umma_selftest: TS mode is bf16, M=128, K in {16,32,64}");
     const size_t smem = (size_t)(dtype == 0 ? 8 : 6) * (size_t)(M * K + N * K);
     TS_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_kernel<<<1, kThreads, smem, tsb::as_stream(stream)>>>(a, b, d, M, N, K, dtype, a_mn, b_mn, swap);
