@@ -38,7 +38,9 @@ constexpr int kMaxAct = 16;
 constexpr int NO = 16;            // padded head width (N of the head GEMM, columns of dOut)
 
 // TMEM column map (fp32 accumulators)
-constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, cDH1 = 192, cDW2 = 256, cDB2 = 320, cDW3 = 352, cDW1 = 384, cDB1 = 448;
+constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, cDH1 = 192, cDW2 = 256, cDW3 = 320, cDB2 = 336, cDB1 = 344, cDW1 = 352;
+// TS-mode A operand (bf16x3 pieces of the CURRENT activation / gradient tile: H1, then H2, then dZ2), 3 x 32 packed columns
+constexpr uint32_t cT = 384, kTPart = 32;
 constexpr uint32_t kTmemCols = 512;
 
 // Optional phase timeline (diagnostics): when g_tc_timeline != nullptr, CTA 0 / thread 0 stores
@@ -96,6 +98,28 @@ __device__ __forceinline__ void store_chunk8(uint8_t* sm0, const Mat& m, uint32_
     *reinterpret_cast<uint4*>(p + 2 * m.part) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
 }
 
+// 16 consecutive columns [c0, c0 + 16) of row r: bf16x3 split once, stored to the shared-memory operand (consumed
+// MN-major by the weight-gradient GEMMs) AND to the thread's TMEM lane (A operand of the next TS-mode GEMM:
+// packed columns t_col + c0 / 2 of each piece).  t_lane_col = 0xffffffff: shared memory only.
+__device__ __forceinline__ void store_row16(uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c0, const float* v,
+                                            uint32_t t_lane_col) {
+    uint32_t w0[8], w1[8], w2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split3_pair(v[2 * j], v[2 * j + 1], w0[j], w1[j], w2[j]);
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        uint8_t* p = sm0 + (m.base + moff(r, c0 + 8 * hlf, m.RS));
+        *reinterpret_cast<uint4*>(p) = make_uint4(w0[4 * hlf], w0[4 * hlf + 1], w0[4 * hlf + 2], w0[4 * hlf + 3]);
+        *reinterpret_cast<uint4*>(p + m.part) = make_uint4(w1[4 * hlf], w1[4 * hlf + 1], w1[4 * hlf + 2], w1[4 * hlf + 3]);
+        *reinterpret_cast<uint4*>(p + 2 * m.part) = make_uint4(w2[4 * hlf], w2[4 * hlf + 1], w2[4 * hlf + 2], w2[4 * hlf + 3]);
+    }
+    if (t_lane_col != 0xffffffffu) {
+        umma::tmem_st8(t_lane_col + (c0 >> 1), w0);
+        umma::tmem_st8(t_lane_col + (c0 >> 1) + kTPart, w1);
+        umma::tmem_st8(t_lane_col + (c0 >> 1) + 2 * kTPart, w2);
+    }
+}
+
 // tanh(x) = 1 - 2 / (exp(2x) + 1) from two MUFU ops; absolute error ~1e-7 (the hidden activations
 // feed 64-term dot products, so absolute -- not relative -- accuracy near 0 is what matters)
 __device__ __forceinline__ float tanh_mufu(float x) {
@@ -113,6 +137,12 @@ __device__ __forceinline__ void gemm(uint32_t d_tmem, int M, int N, const Mat& A
     const uint32_t b_lbo = b_mn ? B.RS : 128u, b_sbo = b_mn ? 128u : B.RS, b_step = b_mn ? 2u * B.RS : 256u;
     umma::gemm_bf16x3_warp<KSTEPS>(d_tmem, A.base, A.part, a_lbo, a_sbo, a_step, B.base, B.part, b_lbo, b_sbo, b_step,
                                    umma::idesc_bf16(M, N, a_mn, b_mn));
+}
+// TS mode: A = the bf16x3 pieces at TMEM columns cT (written by the preceding epilogue), M = 128, K = 64
+__device__ __forceinline__ void gemm_ts(uint32_t tmem, uint32_t d_col, int N, const Mat& B, int b_mn) {
+    const uint32_t b_lbo = b_mn ? B.RS : 128u, b_sbo = b_mn ? 128u : B.RS, b_step = b_mn ? 2u * B.RS : 256u;
+    umma::gemm_bf16x3_ts_warp<H / 16>(tmem + d_col, tmem + cT, kTPart, B.base, B.part, b_lbo, b_sbo, b_step,
+                                      umma::idesc_bf16(128, N, 0, b_mn));
 }
 // runtime K in {16, 32} (padded observation width)
 __device__ __forceinline__ void gemm_kx(uint32_t d_tmem, int M, int N, const Mat& A, int a_mn, const Mat& B, int b_mn, int K) {
@@ -323,6 +353,7 @@ struct Pipe {   // MMA issue / completion handshake
     // control flow) runs `f`, whose MMAs are issued by one elected lane, and commits.
     template <class F>
     __device__ __forceinline__ void run(F&& f) {
+        umma::tmem_wait_st();
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
@@ -349,8 +380,7 @@ __device__ __forceinline__ void epi_tanh(uint8_t* sm0, const Mat& OUT, uint32_t 
     umma::tmem_ld16(tmem + ((32u * (warp & 3)) << 16) + col + c0, h);
 #pragma unroll
     for (int j = 0; j < kCols; ++j) h[j] = tanh_mufu(h[j] + bias[c0 + j]);
-    store_chunk8(sm0, OUT, r, c0, h);
-    store_chunk8(sm0, OUT, r, c0 + 8, h + 8);
+    store_row16(sm0, OUT, r, c0, h, tmem + ((32u * (warp & 3)) << 16) + cT);
 }
 // TMEM dH -> dZ = dH * (1 - h^2) written over ACT (h from registers)
 __device__ __forceinline__ void epi_dtanh(uint8_t* sm0, const Mat& ACT, uint32_t tmem, uint32_t col,
@@ -365,7 +395,7 @@ __device__ __forceinline__ void epi_dtanh(uint8_t* sm0, const Mat& ACT, uint32_t
     store_chunk8(sm0, ACT, r, c0 + 8, v + 8);
 }
 // dZ2 = (dOut W3) * (1 - H2^2) written over H2 (K = out_dim is tiny: SIMT)
-__device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, const Smem& S, int out_dim,
+__device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, int out_dim,
                                                     const float (&h)[kCols]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
@@ -385,8 +415,7 @@ __device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, c
     }
 #pragma unroll
     for (int j = 0; j < kCols; ++j) acc[j] = acc[j] * fmaf(-h[j], h[j], 1.0f);
-    store_chunk8(sm0, S.H2, r, c0, acc);
-    store_chunk8(sm0, S.H2, r, c0 + 8, acc + 8);
+    store_row16(sm0, S.H2, r, c0, acc, tmem + ((32u * (warp & 3)) << 16) + cT);
 }
 // write one row of dOut: fp32 side copy + bf16x3 operand (columns >= out_dim are zero)
 __device__ __forceinline__ void write_dout_row(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t r, const float* dv) {
@@ -482,9 +511,9 @@ __device__ __forceinline__ void trunk_forward(uint8_t* sm, uint8_t* sm0, const S
                                               float (&h1)[kCols], float (&h2)[kCols]) {
     pipe.run([&] { gemm_kx(tmem + cD1, 128, H, S.X, 0, S.W1, 0, S.KXP); });
     epi_tanh(sm0, S.H1, tmem, cD1, reinterpret_cast<const float*>(sm + S.b1), h1);
-    pipe.run([&] { gemm<H / 16>(tmem + cD2, 128, H, S.H1, 0, S.W2, 0); });
+    pipe.run([&] { gemm_ts(tmem, cD2, H, S.W2, 0); });                                 // A = H1 from TMEM
     epi_tanh(sm0, S.H2, tmem, cD2, reinterpret_cast<const float*>(sm + S.b2), h2);
-    pipe.run([&] { gemm<H / 16>(tmem + cD3, 128, NO, S.H2, 0, S.W3, 0); });
+    pipe.run([&] { gemm_ts(tmem, cD3, NO, S.W3, 0); });                                // A = H2 from TMEM
 }
 
 // backward of one trunk given dOut (S.DO / dof); writes all weight and bias gradients of the net.
@@ -496,12 +525,12 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
                                                F&& weights_dead) {
     pipe.run([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });      // dW3^T = H2^T dOut
     tstamp(16);
-    epi_head_input_grad(sm, sm0, S, out_dim, h2);
+    epi_head_input_grad(sm, sm0, S, tmem, out_dim, h2);
     tstamp(17);                                     // H2 := dZ2
     pipe.run([&] {
         gemm<kRows / 16>(tmem + cDW2, 64, H, S.H2, 1, S.H1, 1);                       // dW2 = dZ2^T H1
         gemm_colsum(tmem + cDB2, S.H2, S.ONES, S.ONES_RS);                            // db2 = dZ2^T 1
-        gemm<H / 16>(tmem + cDH1, 128, H, S.H2, 0, S.W2, 1);                          // dH1 = dZ2 W2
+        gemm_ts(tmem, cDH1, H, S.W2, 1);                                              // dH1 = dZ2 W2, A = dZ2 from TMEM
     });
     tstamp(18);
     weights_dead();
