@@ -445,7 +445,7 @@ def main() -> None:
         "e2e_numpy_rng": {"value": e2e_np_value, "unit": "transitions/s", "ms_per_step": ms_np / n_np,
                           "note": "public API with the default minibatch_shuffle='numpy': the reference's np.random.permutation draw per "
                                   "pass (global MT19937 stream, bit-identical minibatch composition) generated on the host by "
-                                  "ts_host_mt19937_permutation -- host-bound at ~4 ms per 524288-element permutation"},
+                                  "background threads of the C library ahead of the passes (ts_host_perm_job_*): ~2 ms per 524288-element permutation"},
         "gpu_launches": int(launches),
         "ingest": ingest,
         "roofline": {"kernel": "ppo_tc_kernel<EPOCH> (persistent: every optimiser step of one pass = minibatch fwd/bwd + "

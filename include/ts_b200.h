@@ -352,6 +352,18 @@ int ts_ppo_epoch_multi(float* params, float* grad, float* partials, float* exp_a
  * Writes int32 directly (e.g. into the pinned upload buffer). */
 int ts_host_mt19937_permutation(uint32_t* key /* in/out */, int32_t* pos /* in/out */, int64_t n, int32_t* out);
 
+/* HOST, asynchronous: all `repeat` permutations of one update() (rows of out[repeat][n], int32, typically pinned),
+ * identical to `repeat` consecutive np.random.permutation(n) draws from the state (key, pos).  A producer thread walks the
+ * MT19937 stream, n_workers threads apply the swaps of different passes concurrently; ts_host_perm_job_wait(job, r)
+ * blocks until row r is complete (rows complete in order of r up to worker interleaving); ts_host_perm_job_finish joins
+ * the threads, returns the advanced generator state (write it back with np.random.set_state) and frees the job.
+ * `out` must stay valid until finish.  Valid because nothing else consumes numpy's global stream inside
+ * Algorithm.update() (batch.py:1209 is its only draw). */
+int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t n, int32_t repeat, int32_t* out, int32_t n_workers,
+                           void** job_out);
+int ts_host_perm_job_wait(void* job, int32_t r);
+int ts_host_perm_job_finish(void* job, uint32_t* key_out, int32_t* pos_out);
+
 /* Device-side minibatch order (opt-in alternative to np.random.permutation, batch.py:1209):
  * out[r*n + i] = pi_r(i), pi_r a keyed bijection of [0,n) (cycle-walking Feistel/Philox). */
 int ts_make_permutation(uint64_t seed, int32_t first_epoch, int32_t n_epochs, int64_t n,

@@ -177,3 +177,22 @@ def test_host_permutation_is_numpy_global_permutation_bit_for_bit():
         out = numpy_global_permutation_(torch.empty(n, dtype=torch.int32))
         assert np.array_equal(out.numpy(), ref), (seed, n)
         assert np.array_equal(np.random.rand(3), ref_next)     # the global stream continues identically
+
+
+def test_permutation_job_matches_numpy_stream():
+    """The background job behind PPO's default minibatch order: rows == consecutive np.random.permutation draws,
+    generator state afterwards == numpy's (product path, host only)."""
+    import torch
+
+    from tianshou_b200.data.batch import NumpyGlobalPermutationJob
+    for seed, n, rep in [(0, 1, 3), (1, 2, 2), (2, 3, 4), (3, 1000, 5), (4, 65537, 3), (5, 200_000, 6)]:
+        np.random.seed(seed)
+        ref = np.stack([np.random.permutation(n) for _ in range(rep)])
+        ref_next = np.random.rand(3)
+        np.random.seed(seed)
+        rows = torch.empty((rep, n), dtype=torch.int32)
+        with NumpyGlobalPermutationJob(rows, rep) as job:
+            for r in reversed(range(rep)):            # any wait order
+                job.wait(r)
+        assert np.array_equal(rows.numpy(), ref), (seed, n)
+        assert np.array_equal(np.random.rand(3), ref_next)

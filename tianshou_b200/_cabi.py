@@ -94,6 +94,9 @@ SIGNATURES: dict[str, list[Any]] = {
                            _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32,
                            C.POINTER(C.c_void_p), _P],
     "ts_host_mt19937_permutation": [_P, C.POINTER(_I32), _I64, _P],
+    "ts_host_perm_job_start": [_P, _I32, _I64, _I32, _P, _I32, C.POINTER(C.c_void_p)],
+    "ts_host_perm_job_wait": [_P, _I32],
+    "ts_host_perm_job_finish": [_P, _P, C.POINTER(_I32)],
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
     "ts_narrow_i64_i32": [_P, _I64, _P, _P],
     "ts_tc_timeline": [_I32, _P],

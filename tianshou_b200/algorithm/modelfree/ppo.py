@@ -27,7 +27,7 @@ import torch
 from ... import ops
 from ..._cabi import STATS_STRIDE, call, ptr, stream_ptr
 from ...data import Batch, ReplayBuffer
-from ...data.batch import minibatch_bounds, numpy_global_permutation_
+from ...data.batch import NumpyGlobalPermutationJob, minibatch_bounds
 from ...parallel import allreduce_sum_, shard_bounds, world
 from ..optim import OptimizerFactory
 from .a2c import A2CTrainingStats, ActorCriticOnPolicyAlgorithm
@@ -90,6 +90,18 @@ class PPO(ActorCriticOnPolicyAlgorithm):
         batch.__dict__["logp_old"] = logp_old
         return batch
 
+    def _one_pass(self, batch: Batch, perm_r: torch.Tensor, bounds: list[tuple[int, int]], hp: Any, stats: torch.Tensor,
+                  r: int, rank: int, wsize: int) -> None:
+        """Pass r over the minibatches in the order ``perm_r`` (optional advantage recompute first, ppo.py:174-178)."""
+        if self.recompute_adv and r > 0:
+            self._add_returns_and_advantages(batch, None, None)
+        if wsize == 1:
+            self._device_passes(batch, perm_r, bounds, hp, stats, 1, False)
+        elif self._peer_exchange(bounds) is not None:
+            self._fused_distributed_pass(batch, perm_r, bounds, hp, stats, rank, wsize)
+        else:
+            self._distributed_repeat(batch, perm_r, bounds, hp, stats, rank, wsize)
+
     def _host_perm_rows(self, repeat: int, n: int) -> torch.Tensor:
         t = self._scratch.get("host_perms")
         if t is None or t.shape[0] < repeat or t.shape[1] != n:
@@ -121,32 +133,19 @@ class PPO(ActorCriticOnPolicyAlgorithm):
         else:
             perms = None
 
-
-        def run_repeats(perm_rows: torch.Tensor, r0: int, nrep: int, recompute: bool) -> None:
-            self._device_passes(batch, perm_rows, bounds, hp, stats[r0 * n_mb:], nrep, recompute)
-
-        if single_call:
-            run_repeats(perms, 0, repeat, self.recompute_adv)
-        else:
-            host_perm = None
+        if single_call:      # every pass of the update in ONE asynchronous C call
+            self._device_passes(batch, perms, bounds, hp, stats, repeat, self.recompute_adv)
+        elif perms is not None:
             for r in range(repeat):
-                if self.recompute_adv and r > 0:
-                    self._add_returns_and_advantages(batch, None, None)
-                if perms is None:
-                    # the reference's RNG draw (np.random.permutation on the global stream, batch.py:1209),
-                    # bit-identical, generated straight into pinned memory and overlapped with the GPU work
-                    # enqueued so far; one pinned row per pass so that a pending async copy is never overwritten
-                    host_perm = self._host_perm_rows(repeat, N)[r]
-                    numpy_global_permutation_(host_perm)
-                    perm_r = host_perm.to(dev, non_blocking=True)
-                else:
-                    perm_r = perms[r]
-                if wsize == 1:
-                    run_repeats(perm_r, r, 1, False)
-                elif self._peer_exchange(bounds) is not None:
-                    self._fused_distributed_pass(batch, perm_r, bounds, hp, stats[r * n_mb:], rank, wsize)
-                else:
-                    self._distributed_repeat(batch, perm_r, bounds, hp, stats[r * n_mb:], rank, wsize)
+                self._one_pass(batch, perms[r], bounds, hp, stats[r * n_mb:], r, rank, wsize)
+        else:
+            # the reference's RNG draws (np.random.permutation on the global stream once per pass, batch.py:1209),
+            # bit-identical, produced ahead of the passes by background threads straight into pinned memory (one row per
+            # pass, so a pending async copy is never overwritten) and overlapped with the GPU work enqueued so far
+            with NumpyGlobalPermutationJob(self._host_perm_rows(repeat, N), repeat) as job:
+                for r in range(repeat):
+                    perm_r = job.wait(r).to(dev, non_blocking=True)
+                    self._one_pass(batch, perm_r, bounds, hp, stats[r * n_mb:], r, rank, wsize)
         result = self._stats_from_device(stats)   # the only host sync of the update
         self._rms_end()
         self._flat.export_state(self.optim._optim)

@@ -68,17 +68,24 @@ extern "C" int ts_host_mt19937_permutation(uint32_t* key, int32_t* pos, int64_t 
                "ts_host_mt19937_permutation: bad arguments");
     int p = *pos;
     for (int64_t i = 0; i < n; ++i) out[i] = (int32_t)i;
-    for (int64_t i = n - 1; i >= 1; --i) {
-        uint32_t mask = (uint32_t)i;
-        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-        uint32_t v;
-        do {   // random_interval: smallest bit mask >= i, reject values > i
-            if (p == kMtN) { mt19937_gen(key); p = 0; }
-            uint32_t y = key[p++];
+    // one iteration per DRAW: a rejected draw (v > i) swaps out[i] with itself and does not advance -- no
+    // data-dependent branch (random_interval's do/while mispredicts ~30 % of the time)
+    int64_t i = n - 1;
+    while (i >= 1) {
+        if (p == kMtN) { mt19937_gen(key); p = 0; }
+        const int avail = kMtN - p;
+        int d = 0;
+        for (; d < avail && i >= 1; ++d) {
+            uint32_t y = key[p + d];
             y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-            v = y & mask;
-        } while (v > (uint32_t)i);
-        const int32_t t = out[v]; out[v] = out[i]; out[i] = t;
+            const uint32_t ui = (uint32_t)i;
+            const uint32_t v = y & (0xffffffffu >> __builtin_clz(ui));
+            const bool ok = v <= ui;
+            const uint32_t vv = ok ? v : ui;
+            const int32_t t = out[vv]; out[vv] = out[i]; out[i] = t;
+            i -= (int64_t)ok;
+        }
+        p += d;
     }
     *pos = p;
     return 0;

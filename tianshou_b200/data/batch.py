@@ -727,3 +727,51 @@ def numpy_global_permutation_(out: "torch.Tensor") -> "torch.Tensor":
     call("ts_host_mt19937_permutation", key.ctypes.data_as(C.c_void_p), C.byref(pos), n, C.c_void_p(out.data_ptr()))
     np.random.set_state((st[0], key, pos.value, st[3], st[4]))
     return out
+
+
+class NumpyGlobalPermutationJob:
+    """All ``repeat`` draws ``np.random.permutation(n)`` of one ``update()`` from numpy's GLOBAL legacy stream,
+    produced ahead of the passes that use them by background threads of the C library
+    (``ts_host_perm_job_*``, csrc/hostperm.cu): bit-identical rows and final generator state, but row r is
+    ready ~4 + 2 r ms after the start instead of after (r + 1) x 14 ms of ``np.random.permutation + astype``.
+    ``rows``: int32 host tensor [>= repeat, n] (pinned).  Use as a context manager; ``wait(r)`` blocks until row r is
+    complete; leaving the context joins the threads and writes the advanced state back into numpy."""
+
+    def __init__(self, rows: "torch.Tensor", repeat: int, n_workers: int | None = None) -> None:
+        import ctypes as C
+        import os
+
+        from .._cabi import call
+        assert rows.dtype == torch.int32 and not rows.is_cuda and rows.is_contiguous() and rows.shape[0] >= repeat
+        self._rows, self._repeat, self._n = rows, repeat, rows.shape[1]
+        self._st = np.random.get_state()
+        self._job = None
+        if self._st[0] != "MT19937":          # not the legacy generator: plain numpy draws, one per wait()
+            return
+        self._key = np.ascontiguousarray(self._st[1], dtype=np.uint32).copy()
+        nw = n_workers or max(1, min(repeat, 4, (os.cpu_count() or 2) // 2))
+        h = C.c_void_p()
+        call("ts_host_perm_job_start", self._key.ctypes.data_as(C.c_void_p), int(self._st[2]), self._n, repeat,
+             C.c_void_p(rows.data_ptr()), nw, C.byref(h))
+        self._job = h
+
+    def wait(self, r: int) -> "torch.Tensor":
+        from .._cabi import call
+        if self._job is None:
+            self._rows[r].copy_(torch.from_numpy(np.random.permutation(self._n).astype(np.int32)))
+        else:
+            call("ts_host_perm_job_wait", self._job, r)
+        return self._rows[r]
+
+    def __enter__(self) -> "NumpyGlobalPermutationJob":
+        return self
+
+    def __exit__(self, *exc: Any) -> None:
+        import ctypes as C
+
+        from .._cabi import call
+        if self._job is not None:
+            pos = C.c_int32(0)
+            call("ts_host_perm_job_finish", self._job, self._key.ctypes.data_as(C.c_void_p), C.byref(pos))
+            self._job = None
+            np.random.set_state((self._st[0], self._key, pos.value, self._st[3], self._st[4]))
