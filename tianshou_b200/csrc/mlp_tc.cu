@@ -79,14 +79,6 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w0, ui
     const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
     w2 = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
 }
-__device__ __forceinline__ void store_elem(uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c, float x) {
-    uint32_t w0, w1, w2;
-    split3_pair(x, 0.0f, w0, w1, w2);
-    uint8_t* p = sm0 + (m.base + moff(r, c, m.RS));
-    *reinterpret_cast<uint16_t*>(p) = (uint16_t)w0;
-    *reinterpret_cast<uint16_t*>(p + m.part) = (uint16_t)w1;
-    *reinterpret_cast<uint16_t*>(p + 2 * m.part) = (uint16_t)w2;
-}
 // 8 consecutive columns (one 16-byte chunk) of row r
 __device__ __forceinline__ void store_chunk8(uint8_t* sm0, const Mat& m, uint32_t r, uint32_t c0, const float* v) {
     uint32_t w0[4], w1[4], w2[4];
@@ -240,25 +232,6 @@ __device__ __forceinline__ void chunk_store(uint8_t* sm0, const Mat& M, int rows
     const int sh = nch == 8 ? 3 : (nch == 4 ? 2 : 1);
     const int task = threadIdx.x;
     if (task < rows * nch) store_chunk8(sm0, M, task >> sh, 8 * (task & (nch - 1)), v);
-}
-
-// Global -> shared staging with U loads in flight per thread (the loads are independent of the
-// stores, so batching them hides the L2 / HBM latency that a load-store-load-store loop exposes).
-template <int U, class LoadF, class StoreF>
-__device__ __forceinline__ void staged_loop(int n, LoadF&& ld, StoreF&& st) {
-    for (int base = 0; base < n; base += kThreads * U) {
-        float v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = base + u * kThreads + (int)threadIdx.x;
-            v[u] = e < n ? ld(e) : 0.0f;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int e = base + u * kThreads + (int)threadIdx.x;
-            if (e < n) st(e, v[u]);
-        }
-    }
 }
 
 // stage one network's weights: bf16x3 blocked copies for the tensor core + fp32 side copies

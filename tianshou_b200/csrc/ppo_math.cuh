@@ -81,15 +81,5 @@ __device__ __forceinline__ float normal_logp_term(float x, float mu, float sigma
     return -(diff * diff) / (2.0f * var) - logf(sigma) - 0.9189385332046727f;
 }
 
-// tanh with ~1e-6 relative accuracy from two MUFU ops (ex2, rcp) + a short odd polynomial near 0
-__device__ __forceinline__ float tanh_fast(float x) {
-    const float ax = fabsf(x);
-    const float x2 = x * x;
-    const float p = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 0.021869488536155203f, -0.053968253968253971f),
-                                               0.13333333333333333f), -0.33333333333333331f), 1.0f);
-    const float e = __expf(2.0f * ax);
-    const float t = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
-    return ax < 0.25f ? p : t;
-}
 
 }  // namespace ppo
