@@ -335,6 +335,24 @@ def main() -> None:
                 ingest["mirror" if mirror else "host_only"] = {
                     "add_ms_per_call": 1e3 * (t1 - t0) / (T - 1), "transitions_per_s": E * (T - 1) / (t1 - t0),
                     "drain_ms_after_last_add": 1e3 * (t2 - t1)}
+            # Collector-side policy inference: policy(Batch(obs=[E, obs])) from host numpy, actions
+            # read back, fused forward kernel vs the torch module-by-module forward
+            from tianshou_b200.data import Batch as _B
+            obs_host = steps_host[0].obs
+            infer = {}
+            for fused_on in (False, True):
+                algo.policy.use_fused_inference = fused_on
+                with torch.no_grad():
+                    for _ in range(5):
+                        algo.policy(_B(obs=obs_host, info=_B())).act.cpu()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(50):
+                        algo.policy(_B(obs=obs_host, info=_B())).act.cpu()
+                    infer["fused_kernel" if fused_on else "torch_modules"] = 1e6 * (time.perf_counter() - t0) / 50
+            algo.policy.use_fused_inference = True
+            ingest["policy_forward_us_per_call"] = infer | {"rows": int(E)}
+
             def e2e_mirrored_step():
                 algo.update(buffer=mb, batch_size=BATCH_SIZE, repeat=REPEAT)
             e2e_mirrored_step()

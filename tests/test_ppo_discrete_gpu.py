@@ -131,3 +131,16 @@ def test_discrete_grad_kernel_vs_oracle():
         np.testing.assert_allclose(got, grads[k], rtol=2e-4, atol=2e-6, err_msg=k)
     ex = gflat[algo._desc.n_params:]
     np.testing.assert_allclose([-ex[0] / n, ex[1] / n, ex[2] / n], ls[1:], rtol=2e-5, atol=1e-6)
+
+
+def test_discrete_policy_forward_fused_inference():
+    from tianshou_b200.data import Batch
+    g = load_golden("ppo_ref_C1.npz")
+    algo, actor, critic = build_discrete(g, DEV)
+    pol = algo.policy
+    obs = np.random.default_rng(1).standard_normal((77, 4)).astype(np.float32)
+    with torch.no_grad():
+        fused = pol(Batch(obs=obs, info=Batch())).logits
+        pol.use_fused_inference = False
+        ref = pol(Batch(obs=obs, info=Batch())).logits
+    np.testing.assert_allclose(fused.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-6)

@@ -261,3 +261,28 @@ def test_large_rollout_update_vs_oracle():
         np.testing.assert_allclose(pv.detach().cpu().numpy(), p[k], rtol=2e-3, atol=3e-5, err_msg=k)
     np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var, algo.ret_rms.count],
                                [rms.mean, rms.var, rms.count], rtol=1e-5)
+
+
+def test_policy_forward_fused_inference_matches_torch_modules():
+    """Collector-side ``policy(batch)`` (reinforce.py:167-192): under no_grad the actor output comes from the fused
+    forward kernel; it must agree with the torch module forward, keep the Batch structure, and leave autograd alone."""
+    from tianshou_b200.data import Batch
+    g = load_golden("ppo_ref_A.npz")
+    algo, actor, critic = build_ppo(17, 6, DEV, params={k: g["p0_" + k] for k in PARAM_ORDER}, **ppo_kwargs(g))
+    pol = algo.policy
+    assert pol._fused_inference is not None
+    obs = np.random.default_rng(0).standard_normal((300, 17)).astype(np.float32)
+    with torch.no_grad():
+        torch.manual_seed(0)
+        fused = pol(Batch(obs=obs, info=Batch()))
+        pol.use_fused_inference = False
+        torch.manual_seed(0)
+        ref = pol(Batch(obs=obs, info=Batch()))
+        pol.use_fused_inference = True
+    (mu_f, sig_f), (mu_r, sig_r) = fused.logits, ref.logits
+    np.testing.assert_allclose(mu_f.cpu().numpy(), mu_r.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    assert torch.equal(sig_f, sig_r) and fused.act.shape == ref.act.shape == (300, 6)
+    np.testing.assert_allclose(fused.act.cpu().numpy(), ref.act.cpu().numpy(), rtol=1e-4, atol=1e-5)   # same torch RNG draw
+    assert fused.state is None and isinstance(fused.dist, torch.distributions.Independent)
+    out = pol(Batch(obs=obs, info=Batch()))              # grad enabled: the torch modules run (autograd graph intact)
+    assert out.logits[0].requires_grad

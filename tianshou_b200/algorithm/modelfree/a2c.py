@@ -87,6 +87,8 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         from ..._cabi import load_library
         nbytes = int(load_library().ts_ppo_weight_image_bytes(_C.byref(self._desc)))
         self._flat.weight_image = torch.zeros(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
+        if hasattr(self.policy, "_fused_inference"):      # Collector-side inference through the same forward kernel
+            self.policy._fused_inference = (self._flat, self._desc)
         if self._world_size() > 1:  # replicas start bit-identical
             from ...parallel import broadcast_params_
             broadcast_params_(self._flat.flat)
