@@ -224,8 +224,10 @@ def test_device_shuffle_is_a_permutation_and_trains():
     np.testing.assert_allclose(stats.vf_loss.mean, g["u0_losses"][:, 2].mean(), rtol=0.05)
 
 
-def test_large_rollout_update_vs_oracle():
-    """Config-2-shaped slice (512 envs x 128 steps) through the public API vs the numpy oracle."""
+@pytest.mark.parametrize("bs", [16384, 32768, None])   # 128 tiles (one per CTA), 256 and 512 tiles (several per CTA)
+def test_large_rollout_update_vs_oracle(bs):
+    """Config-2-shaped slice (512 envs x 128 steps) through the public API vs the numpy oracle; the larger
+    minibatches exercise the multi-tile-per-CTA path of the persistent kernel (gradient rows accumulated, not stored)."""
     from tianshou_b200.data import Batch, VectorReplayBuffer
     from tianshou_b200.utils import policy_within_training_step
     E, T = 512, 128
@@ -250,11 +252,11 @@ def test_large_rollout_update_vs_oracle():
     hp = dict(eps_clip=0.2, dual_clip=None, vf_coef=0.25, ent_coef=0.0, max_grad_norm=0.5, adv_eps=1e-8, value_clip=True,
               advantage_normalization=False, lr=3e-4, beta1=0.9, beta2=0.999, adam_eps=1e-8, weight_decay=0.0)
     rms = onp.RunningMeanStd()
-    res = onp.ppo_update(p, m, v, 0, roll, perms, 16384, 2, hp, rms, 0.99, 0.95, True)
+    res = onp.ppo_update(p, m, v, 0, roll, perms, bs, 2, hp, rms, 0.99, 0.95, True)
     np.random.seed(0)
     with policy_within_training_step(algo.policy):
-        stats = algo.update(buffer=buf, batch_size=16384, repeat=2)
-    assert stats.gradient_steps == 8
+        stats = algo.update(buffer=buf, batch_size=bs, repeat=2)
+    assert stats.gradient_steps == 2 * (N // bs if bs else 1)
     np.testing.assert_allclose(stats.loss.mean, res["losses"][:, 0].mean(), rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(stats.vf_loss.mean, res["losses"][:, 2].mean(), rtol=1e-3, atol=1e-5)
     for k, pv in named_params(actor, critic).items():
