@@ -288,3 +288,41 @@ def test_policy_forward_fused_inference_matches_torch_modules():
     assert fused.state is None and isinstance(fused.dist, torch.distributions.Independent)
     out = pol(Batch(obs=obs, info=Batch()))              # grad enabled: the torch modules run (autograd graph intact)
     assert out.logits[0].requires_grad
+
+
+def test_wide_observation_runs_simt_kernels_vs_oracle():
+    """obs_dim = 40 is outside the tensor-core kernels' envelope (<= 32): value / log-prob passes and the whole update run
+    the fp32 SIMT kernels (per-step ts_ppo_grad -> ts_clip_adam_step); same parity bar against the numpy oracle."""
+    from tianshou_b200.data import Batch, VectorReplayBuffer
+    from tianshou_b200.utils import policy_within_training_step
+    E, T, OBS, ACT = 24, 20, 40, 5
+    kw = dict(gamma=0.99, gae_lambda=0.95, max_grad_norm=0.5, vf_coef=0.25, ent_coef=0.01, return_scaling=True,
+              eps_clip=0.2, value_clip=True, dual_clip=None, advantage_normalization=True, recompute_advantage=True)
+    algo, actor, critic = build_ppo(OBS, ACT, DEV, **kw)
+    assert algo._flat.weight_image is None            # no tensor-core path for this shape
+    p = {k: v.detach().cpu().numpy().copy() for k, v in named_params(actor, critic).items()}
+    buf = VectorReplayBuffer(E * T, E, device=DEV)
+    for s in synth_rollout(np.random.default_rng(3), E, T, OBS, ACT, p_term=0.03, trunc_len=15):
+        buf.add(Batch(**s), buffer_ids=np.arange(E))
+    N = E * T
+    unf = np.zeros(N, dtype=bool)
+    last = np.arange(E) * T + T - 1
+    unf[last] = ~buf.done[last]
+    roll = dict(obs=buf.obs.copy(), obs_next=buf.obs_next.copy(), act=buf.act.copy(), rew=buf.rew.copy(),
+                terminated=buf.terminated.copy(), truncated=buf.truncated.copy(), unfinished=unf)
+    np.random.seed(4)
+    perms = np.stack([np.random.permutation(N) for _ in range(2)])
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(vv) for k, vv in p.items()}
+    hp = dict(eps_clip=0.2, dual_clip=None, vf_coef=0.25, ent_coef=0.01, max_grad_norm=0.5, adv_eps=1e-8, value_clip=True,
+              advantage_normalization=True, lr=3e-4, beta1=0.9, beta2=0.999, adam_eps=1e-8, weight_decay=0.0)
+    rms = onp.RunningMeanStd()
+    res = onp.ppo_update(p, m, v, 0, roll, perms, 100, 2, hp, rms, 0.99, 0.95, True)
+    np.random.seed(4)
+    with policy_within_training_step(algo.policy):
+        stats = algo.update(buffer=buf, batch_size=100, repeat=2)
+    assert stats.gradient_steps == res["losses"].shape[0]
+    for col, name in enumerate(["loss", "actor_loss", "vf_loss", "ent_loss"]):
+        np.testing.assert_allclose(getattr(stats, name).mean, res["losses"][:, col].mean(), rtol=1e-3, atol=2e-5, err_msg=name)
+    for k, pv in named_params(actor, critic).items():
+        np.testing.assert_allclose(pv.detach().cpu().numpy(), p[k], rtol=2e-3, atol=3e-5, err_msg=k)
