@@ -99,14 +99,32 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
                                       int32_t n_workers, void** job_out) {
     TS_REQUIRE(key && out && job_out && n >= 0 && n <= 0x7fffffffLL && repeat >= 1 && pos >= 0 && pos <= kMtN,
                "ts_host_perm_job_start: bad arguments");
-    PermJob* job = new PermJob();
-    std::memcpy(job->key, key, sizeof(job->key));
-    job->pos = pos; job->n = n; job->repeat = repeat; job->out = out;
-    job->js.resize((size_t)repeat);
-    job->state.assign((size_t)repeat, 0);
-    const int nw = n_workers < 1 ? 1 : (n_workers > repeat ? repeat : n_workers);
-    job->producer = std::thread([job] { job->produce(); });
-    for (int w = 0; w < nw; ++w) job->workers.emplace_back([job] { job->apply_loop(); });
+    PermJob* job = nullptr;
+    try {
+        job = new PermJob();
+        std::memcpy(job->key, key, sizeof(job->key));
+        job->pos = pos; job->n = n; job->repeat = repeat; job->out = out;
+        job->js.resize((size_t)repeat);
+        job->state.assign((size_t)repeat, 0);
+        const int nw = n_workers < 1 ? 1 : (n_workers > repeat ? repeat : n_workers);
+        job->producer = std::thread([job] { job->produce(); });
+        for (int w = 0; w < nw; ++w) {
+            try {
+                job->workers.emplace_back([job] { job->apply_loop(); });
+            } catch (const std::exception&) {
+                if (job->workers.empty()) throw;      // no worker at all: give up; otherwise run with fewer
+                break;
+            }
+        }
+    } catch (const std::exception& e) {     // out of memory / thread limit: the caller falls back to the serial draw
+        if (job) {
+            if (job->producer.joinable()) job->producer.join();
+            for (auto& w : job->workers) w.join();
+            delete job;
+        }
+        tsb::set_error("ts_host_perm_job_start: %s", e.what());
+        return 1;
+    }
     *job_out = job;
     return 0;
 }

@@ -746,20 +746,27 @@ class NumpyGlobalPermutationJob:
         self._rows, self._repeat, self._n = rows, repeat, rows.shape[1]
         self._st = np.random.get_state()
         self._job = None
-        if self._st[0] != "MT19937":          # not the legacy generator: plain numpy draws, one per wait()
+        if self._st[0] != "MT19937":          # not the legacy MT19937 state: plain numpy draws, in order, up front
+            self._draw_serially()
             return
         self._key = np.ascontiguousarray(self._st[1], dtype=np.uint32).copy()
         nw = n_workers or max(1, min(repeat, 4, (os.cpu_count() or 2) // 2))
         h = C.c_void_p()
-        call("ts_host_perm_job_start", self._key.ctypes.data_as(C.c_void_p), int(self._st[2]), self._n, repeat,
-             C.c_void_p(rows.data_ptr()), nw, C.byref(h))
-        self._job = h
+        try:
+            call("ts_host_perm_job_start", self._key.ctypes.data_as(C.c_void_p), int(self._st[2]), self._n, repeat,
+                 C.c_void_p(rows.data_ptr()), nw, C.byref(h))
+            self._job = h
+        except RuntimeError:      # no threads / memory for the job: same stream, drawn serially (in order) right now
+            self._job = None
+            self._draw_serially()
+
+    def _draw_serially(self) -> None:
+        for r in range(self._repeat):
+            numpy_global_permutation_(self._rows[r])
 
     def wait(self, r: int) -> "torch.Tensor":
         from .._cabi import call
-        if self._job is None:
-            self._rows[r].copy_(torch.from_numpy(np.random.permutation(self._n).astype(np.int32)))
-        else:
+        if self._job is not None:
             call("ts_host_perm_job_wait", self._job, r)
         return self._rows[r]
 
