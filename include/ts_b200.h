@@ -225,7 +225,11 @@ typedef struct ts_ppo_hparams {
     double lr, beta1, beta2, adam_eps, weight_decay;
     int32_t value_clip;
     int32_t advantage_normalization;
+    int32_t loss_kind;    /* TS_LOSS_PPO (0): clipped surrogate, ppo.py:184-196; TS_LOSS_A2C (1): actor loss
+                           * -mean(log_prob * adv) (a2c.py:262-266), eps_clip / dual_clip / logp_old / v_s unused */
 } ts_ppo_hparams;
+#define TS_LOSS_PPO 0
+#define TS_LOSS_A2C 1
 
 /* Per-optimiser-step device statistics: {loss, clip_loss, vf_loss, ent_loss, grad_norm, n_rows,
  * 0, 0} -- 8 floats per step (ppo.py:213-216 without the 4 host syncs). */

@@ -497,9 +497,71 @@ def gen_ppo_discrete():
         print(f"ppo_ref_{name}.npz", len(out), "arrays; gradient_steps", int(out["u0_gradient_steps"]))
 
 
+def gen_a2c():
+    """Reference A2C (a2c.py:156-299) on the MuJoCo-shaped nets: same capture as gen_ppo (no logp_old)."""
+    import tianshou.algorithm.modelfree.a2c as ref_a2c
+    from tianshou.algorithm import A2C
+    obs_dim, act_dim = 17, 6
+    cfg = dict(E=16, cap=32, steps=32, bs=128, repeat=2, seed=5,
+               kw=dict(gamma=0.99, gae_lambda=0.95, max_grad_norm=0.5, vf_coef=0.5, ent_coef=0.01, return_scaling=True))
+    rng = np.random.default_rng(500)
+    ppo_algo, actor, critic = build_ref_ppo(obs_dim, act_dim, cfg["seed"])       # nets + policy, PPO wrapper discarded
+    algo = A2C(policy=ppo_algo.policy, critic=critic, optim=AdamOptimizerFactory(lr=3e-4), **cfg["kw"])
+    steps = synth_rollout(rng, cfg["E"], cfg["steps"], obs_dim, act_dim, 0.03, 20)
+    steps2 = synth_rollout(rng, cfg["E"], cfg["steps"], obs_dim, act_dim, 0.03, 20)
+    buf = VectorReplayBuffer(cfg["E"] * cfg["cap"], cfg["E"])
+    fill(buf, steps)
+    out = {"p0_" + k: v.detach().numpy().copy() for k, v in flat_named_params(actor, critic).items()}
+    captured = {"pre": [], "seq": []}
+    orig_pre = algo._preprocess_batch
+
+    def pre_hook(batch, buffer, indices):
+        b = orig_pre(batch, buffer, indices)
+        captured["pre"].append({k: b[k].detach().numpy().copy() for k in ("v_s", "returns", "adv")}
+                               | {"indices": np.asarray(indices).copy()})
+        return b
+
+    algo._preprocess_batch = pre_hook
+    orig_from = ref_a2c.SequenceSummaryStats.from_sequence
+
+    def rec(seq):
+        captured["seq"].append(np.asarray(seq, dtype=np.float64))
+        return orig_from(seq)
+
+    ref_a2c.SequenceSummaryStats.from_sequence = rec
+    for u, st in enumerate([steps, steps2]):
+        if u == 1:
+            buf.reset(keep_statistics=True)
+            fill(buf, st)
+        np.random.seed(1000 + u)
+        torch.manual_seed(2000 + u)
+        N = len(buf)
+        with policy_within_training_step(algo.policy):
+            stats = algo.update(buffer=buf, batch_size=cfg["bs"], repeat=cfg["repeat"])
+        np.random.seed(1000 + u)
+        perms = np.stack([np.random.permutation(N) for _ in range(cfg["repeat"])])
+        pre = captured["pre"][u]
+        seqs = captured["seq"][4 * u: 4 * u + 4]
+        o = f"u{u}_"
+        out.update({o + "perms": perms, o + "indices": pre["indices"], o + "v_s": pre["v_s"], o + "returns": pre["returns"],
+                    o + "adv": pre["adv"], o + "losses": np.stack(seqs, axis=1), o + "gradient_steps": stats.gradient_steps,
+                    o + "rms": np.array([float(algo.ret_rms.mean), float(algo.ret_rms.var), float(algo.ret_rms.count)])})
+        out.update({o + "p_" + k: v.detach().numpy().copy() for k, v in flat_named_params(actor, critic).items()})
+        for key in ("obs", "act", "rew", "terminated", "truncated", "obs_next", "done"):
+            out[o + "buf_" + key] = np.asarray(buf._meta[key]).copy()
+        out.update({o + "meta_" + k: v for k, v in meta_of(buf).items()})
+        out[o + "unfinished"] = buf.unfinished_index()
+    ref_a2c.SequenceSummaryStats.from_sequence = orig_from
+    out["cfg_E"], out["cfg_cap"], out["cfg_steps"], out["cfg_bs"], out["cfg_repeat"] = cfg["E"], cfg["cap"], cfg["steps"], cfg["bs"], cfg["repeat"]
+    for k, v in cfg["kw"].items():
+        out["kw_" + k] = np.nan if v is None else v
+    np.savez_compressed(os.path.join(OUT, "a2c_ref.npz"), **out)
+    print("a2c_ref.npz", len(out), "arrays; gradient_steps", int(out["u0_gradient_steps"]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["returns", "index", "segtree", "ppo", "ppo_discrete"]
+    which = sys.argv[1:] or ["returns", "index", "segtree", "ppo", "ppo_discrete", "a2c"]
     for w in which:
         {"returns": gen_returns, "index": gen_index, "segtree": gen_segtree, "ppo": gen_ppo,
-         "ppo_discrete": gen_ppo_discrete}[w]()
+         "ppo_discrete": gen_ppo_discrete, "a2c": gen_a2c}[w]()

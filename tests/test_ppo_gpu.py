@@ -326,3 +326,34 @@ def test_wide_observation_runs_simt_kernels_vs_oracle():
         np.testing.assert_allclose(getattr(stats, name).mean, res["losses"][:, col].mean(), rtol=1e-3, atol=2e-5, err_msg=name)
     for k, pv in named_params(actor, critic).items():
         np.testing.assert_allclose(pv.detach().cpu().numpy(), p[k], rtol=2e-3, atol=3e-5, err_msg=k)
+
+
+def test_a2c_update_matches_reference():
+    """A2C through the same persistent kernel (TS_LOSS_A2C) vs the imported reference's A2C run (tests/golden/a2c_ref.npz)."""
+    from tianshou_b200.algorithm import A2C, AdamOptimizerFactory, ProbabilisticActorPolicy
+    from tianshou_b200.algorithm.modelfree.a2c import A2C as A2C_via_ref_path
+    from tianshou_b200.utils import policy_within_training_step
+    from ts_testutil import Box, build_actor_critic, gaussian_dist, load_params
+    assert A2C_via_ref_path is A2C
+    g = load_golden("a2c_ref.npz")
+    actor, critic = build_actor_critic(17, 6, DEV)
+    load_params(actor, critic, {k: g["p0_" + k] for k in PARAM_ORDER})
+    policy = ProbabilisticActorPolicy(actor=actor, dist_fn=gaussian_dist, action_scaling=True, action_bound_method="clip",
+                                      action_space=Box(6))
+    algo = A2C(policy=policy, critic=critic, optim=AdamOptimizerFactory(lr=3e-4), gamma=float(g["kw_gamma"]),
+               gae_lambda=float(g["kw_gae_lambda"]), max_grad_norm=float(g["kw_max_grad_norm"]),
+               vf_coef=float(g["kw_vf_coef"]), ent_coef=float(g["kw_ent_coef"]), return_scaling=bool(g["kw_return_scaling"]))
+    E, cap = int(g["cfg_E"]), int(g["cfg_cap"])
+    for u in range(2):
+        o = f"u{u}_"
+        buf = restore_vector_buffer(g, o, E, cap, device=DEV)
+        np.random.seed(1000 + u)
+        with policy_within_training_step(algo.policy):
+            stats = algo.update(buffer=buf, batch_size=int(g["cfg_bs"]), repeat=int(g["cfg_repeat"]))
+        assert stats.gradient_steps == int(g[o + "gradient_steps"])
+        ref_losses = g[o + "losses"]
+        for col, name in enumerate(["loss", "actor_loss", "vf_loss", "ent_loss"]):
+            np.testing.assert_allclose(getattr(stats, name).mean, ref_losses[:, col].mean(), rtol=5e-4, atol=2e-5, err_msg=name)
+        for k, pv in named_params(actor, critic).items():
+            np.testing.assert_allclose(pv.detach().cpu().numpy(), g[o + "p_" + k], rtol=2e-3, atol=3e-5, err_msg=f"a2c u{u} {k}")
+        np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var, algo.ret_rms.count], g[o + "rms"], rtol=1e-5)

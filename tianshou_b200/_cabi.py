@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libts_b200.so")
 
 TS_F32, TS_F64 = 0, 1
 AC_RELU, AC_CATEGORICAL = 1, 2
+LOSS_PPO, LOSS_A2C = 0, 1
 STATS_STRIDE = 8
 GRAD_EXTRA = 4
 
@@ -43,7 +44,7 @@ class PPOHParams(C.Structure):
         ("ent_coef", C.c_double), ("max_grad_norm", C.c_double), ("adv_eps", C.c_double),
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
         ("weight_decay", C.c_double),
-        ("value_clip", C.c_int32), ("advantage_normalization", C.c_int32), ("reserved", C.c_int32),
+        ("value_clip", C.c_int32), ("advantage_normalization", C.c_int32), ("loss_kind", C.c_int32),
     ]
 
 

@@ -244,3 +244,12 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
 
     def _alloc_stats(self, rows: int) -> torch.Tensor:
         return torch.zeros((rows, STATS_STRIDE), dtype=torch.float32, device=self.device)
+
+
+def __getattr__(name: str) -> Any:
+    """``A2C`` shares the fused update loop with PPO and lives next to it (ppo.py imports this module, so the
+    reference's import path ``...modelfree.a2c.A2C`` is served lazily)."""
+    if name == "A2C":
+        from .ppo import A2C
+        return A2C
+    raise AttributeError(name)

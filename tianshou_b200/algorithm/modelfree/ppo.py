@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from ... import ops
-from ..._cabi import STATS_STRIDE, call, ptr, stream_ptr
+from ..._cabi import LOSS_A2C, STATS_STRIDE, call, ptr, stream_ptr
 from ...data import Batch, ReplayBuffer
 from ...data.batch import NumpyGlobalPermutationJob, minibatch_bounds
 from ...parallel import allreduce_sum_, shard_bounds, world
@@ -34,61 +34,19 @@ from .a2c import A2CTrainingStats, ActorCriticOnPolicyAlgorithm
 from .reinforce import ProbabilisticActorPolicy
 
 
-class PPO(ActorCriticOnPolicyAlgorithm):
-    """Proximal Policy Optimization (arXiv:1707.06347), clip variant with optional dual clip,
-    value clip, advantage normalisation and per-repeat advantage recomputation."""
+class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
+    """The repeat x minibatch loop shared by PPO and A2C as device work: per pass ONE persistent launch covering every
+    optimiser step (single GPU), the same launch with the gradient all-reduce fused in (multi GPU, NVLink peer memory),
+    or the per-step NCCL fallback.  Subclasses provide ``_preprocess_batch`` and ``_loss_hparams``."""
 
-    def __init__(
-        self,
-        *,
-        policy: ProbabilisticActorPolicy,
-        critic: torch.nn.Module,
-        optim: OptimizerFactory,
-        eps_clip: float = 0.2,
-        dual_clip: float | None = None,
-        value_clip: bool = False,
-        advantage_normalization: bool = True,
-        recompute_advantage: bool = False,
-        vf_coef: float = 0.5,
-        ent_coef: float = 0.01,
-        max_grad_norm: float | None = None,
-        gae_lambda: float = 0.95,
-        max_batchsize: int = 256,
-        gamma: float = 0.99,
-        return_scaling: bool = False,
-        minibatch_shuffle: Literal["numpy", "device"] = "numpy",
-        shuffle_seed: int = 0,
-    ) -> None:
-        assert dual_clip is None or dual_clip > 1.0, (
-            f"Dual-clip PPO parameter should greater than 1.0 but got {dual_clip}")
-        super().__init__(policy=policy, critic=critic, optim=optim, optim_include_actor=True,
-                         max_grad_norm=max_grad_norm, gae_lambda=gae_lambda, max_batchsize=max_batchsize,
-                         gamma=gamma, return_scaling=return_scaling)
-        self.vf_coef = vf_coef
-        self.ent_coef = ent_coef
-        self.eps_clip = eps_clip
-        self.dual_clip = dual_clip
-        self.value_clip = value_clip
-        self.advantage_normalization = advantage_normalization
-        self.recompute_adv = recompute_advantage
-        if minibatch_shuffle not in ("numpy", "device"):
-            raise ValueError(f"minibatch_shuffle must be 'numpy' or 'device', got {minibatch_shuffle!r}")
-        self.minibatch_shuffle = minibatch_shuffle
-        self._shuffle_seed = shuffle_seed
-        self._shuffle_epoch = 0
+    minibatch_shuffle: str = "numpy"
+    _shuffle_seed: int = 0
+    _shuffle_epoch: int = 0
+    recompute_adv: bool = False
+    advantage_normalization: bool = False
 
-    # ------------------------------------------------------------------ preprocess
-    def _preprocess_batch(self, batch: Batch, buffer: ReplayBuffer, indices: Any) -> Batch:
-        """returns / advantages / logp_old on the device (ppo.py:146-162)."""
-        self._rms_begin()
-        if self.recompute_adv:
-            self._buffer, self._indices = buffer, indices
-        batch = self._add_returns_and_advantages(batch, buffer, indices)
-        n = batch.obs.shape[0]
-        logp_old = self._buf("logp_old", n, torch.float32)
-        ops.actor_logp(self._flat.flat, self._desc, batch.obs, batch.act, out=logp_old)
-        batch.__dict__["logp_old"] = logp_old
-        return batch
+    def _loss_hparams(self) -> Any:
+        raise NotImplementedError
 
     def _one_pass(self, batch: Batch, perm_r: torch.Tensor, bounds: list[tuple[int, int]], hp: Any, stats: torch.Tensor,
                   r: int, rank: int, wsize: int) -> None:
@@ -108,12 +66,6 @@ class PPO(ActorCriticOnPolicyAlgorithm):
             t = self._scratch["host_perms"] = torch.empty((repeat, n), dtype=torch.int32, pin_memory=True)
         return t
 
-    def _ppo_hparams(self):
-        return self._hparams(
-            eps_clip=float(self.eps_clip), dual_clip=float(self.dual_clip or 0.0), vf_coef=float(self.vf_coef),
-            ent_coef=float(self.ent_coef), value_clip=int(bool(self.value_clip)),
-            advantage_normalization=int(bool(self.advantage_normalization)))
-
     # ------------------------------------------------------------------ update
     def _update_with_batch(self, batch: Batch, batch_size: int | None, repeat: int) -> A2CTrainingStats:
         """The repeat x minibatch loop of ppo.py:164-224 as device work."""
@@ -122,7 +74,7 @@ class PPO(ActorCriticOnPolicyAlgorithm):
         size = batch_size or N
         bounds = minibatch_bounds(N, size, merge_last=True)
         n_mb = len(bounds)
-        hp = self._ppo_hparams()
+        hp = self._loss_hparams()
         stats = self._alloc_stats(repeat * n_mb)
         rank, wsize = world()
         single_call = self.minibatch_shuffle == "device" and wsize == 1
@@ -234,3 +186,100 @@ class PPO(ActorCriticOnPolicyAlgorithm):
             allreduce_sum_(f.grad)   # ONE collective per optimiser step: grads + loss sums
             call("ts_clip_adam_step", ptr(f.flat), ptr(f.grad), None, 0, ptr(f.exp_avg), ptr(f.exp_avg_sq), ptr(f.step),
                  C.byref(self._desc), C.byref(hp), ptr(stats[m]), st)
+
+
+
+class PPO(FusedActorCriticUpdate):
+    """Proximal Policy Optimization (arXiv:1707.06347), clip variant with optional dual clip,
+    value clip, advantage normalisation and per-repeat advantage recomputation."""
+
+    def __init__(
+        self,
+        *,
+        policy: ProbabilisticActorPolicy,
+        critic: torch.nn.Module,
+        optim: OptimizerFactory,
+        eps_clip: float = 0.2,
+        dual_clip: float | None = None,
+        value_clip: bool = False,
+        advantage_normalization: bool = True,
+        recompute_advantage: bool = False,
+        vf_coef: float = 0.5,
+        ent_coef: float = 0.01,
+        max_grad_norm: float | None = None,
+        gae_lambda: float = 0.95,
+        max_batchsize: int = 256,
+        gamma: float = 0.99,
+        return_scaling: bool = False,
+        minibatch_shuffle: Literal["numpy", "device"] = "numpy",
+        shuffle_seed: int = 0,
+    ) -> None:
+        assert dual_clip is None or dual_clip > 1.0, (
+            f"Dual-clip PPO parameter should greater than 1.0 but got {dual_clip}")
+        super().__init__(policy=policy, critic=critic, optim=optim, optim_include_actor=True,
+                         max_grad_norm=max_grad_norm, gae_lambda=gae_lambda, max_batchsize=max_batchsize,
+                         gamma=gamma, return_scaling=return_scaling)
+        self.vf_coef = vf_coef
+        self.ent_coef = ent_coef
+        self.eps_clip = eps_clip
+        self.dual_clip = dual_clip
+        self.value_clip = value_clip
+        self.advantage_normalization = advantage_normalization
+        self.recompute_adv = recompute_advantage
+        if minibatch_shuffle not in ("numpy", "device"):
+            raise ValueError(f"minibatch_shuffle must be 'numpy' or 'device', got {minibatch_shuffle!r}")
+        self.minibatch_shuffle = minibatch_shuffle
+        self._shuffle_seed = shuffle_seed
+        self._shuffle_epoch = 0
+
+    # ------------------------------------------------------------------ preprocess
+    def _preprocess_batch(self, batch: Batch, buffer: ReplayBuffer, indices: Any) -> Batch:
+        """returns / advantages / logp_old on the device (ppo.py:146-162)."""
+        self._rms_begin()
+        if self.recompute_adv:
+            self._buffer, self._indices = buffer, indices
+        batch = self._add_returns_and_advantages(batch, buffer, indices)
+        n = batch.obs.shape[0]
+        logp_old = self._buf("logp_old", n, torch.float32)
+        ops.actor_logp(self._flat.flat, self._desc, batch.obs, batch.act, out=logp_old)
+        batch.__dict__["logp_old"] = logp_old
+        return batch
+
+    def _ppo_hparams(self):
+        return self._hparams(
+            eps_clip=float(self.eps_clip), dual_clip=float(self.dual_clip or 0.0), vf_coef=float(self.vf_coef),
+            ent_coef=float(self.ent_coef), value_clip=int(bool(self.value_clip)),
+            advantage_normalization=int(bool(self.advantage_normalization)))
+
+    _loss_hparams = _ppo_hparams
+
+
+class A2C(FusedActorCriticUpdate):
+    """Synchronous Advantage Actor-Critic (arXiv:1602.01783); reference: a2c.py:156-299.  Same device path as PPO with
+    the actor loss ``-(log_prob * adv).mean()`` (``TS_LOSS_A2C``), plain MSE value loss, no clipping."""
+
+    def __init__(self, *, policy: ProbabilisticActorPolicy, critic: torch.nn.Module, optim: OptimizerFactory,
+                 vf_coef: float = 0.5, ent_coef: float = 0.01, max_grad_norm: float | None = None,
+                 gae_lambda: float = 0.95, max_batchsize: int = 256, gamma: float = 0.99, return_scaling: bool = False,
+                 minibatch_shuffle: Literal["numpy", "device"] = "numpy", shuffle_seed: int = 0) -> None:
+        super().__init__(policy=policy, critic=critic, optim=optim, optim_include_actor=True,
+                         max_grad_norm=max_grad_norm, gae_lambda=gae_lambda, max_batchsize=max_batchsize,
+                         gamma=gamma, return_scaling=return_scaling)
+        self.vf_coef = vf_coef
+        self.ent_coef = ent_coef
+        if minibatch_shuffle not in ("numpy", "device"):
+            raise ValueError(f"minibatch_shuffle must be 'numpy' or 'device', got {minibatch_shuffle!r}")
+        self.minibatch_shuffle = minibatch_shuffle
+        self._shuffle_seed = shuffle_seed
+
+    def _preprocess_batch(self, batch: Batch, buffer: ReplayBuffer, indices: Any) -> Batch:
+        """returns / advantages on the device (a2c.py:239-247); the A2C loss needs no behaviour log-prob."""
+        self._rms_begin()
+        batch = self._add_returns_and_advantages(batch, buffer, indices)
+        n = batch.obs.shape[0]
+        batch.__dict__["logp_old"] = self._buf("logp_old", n, torch.float32).zero_()     # unused by TS_LOSS_A2C
+        return batch
+
+    def _loss_hparams(self) -> Any:
+        return self._hparams(eps_clip=0.0, dual_clip=0.0, vf_coef=float(self.vf_coef), ent_coef=float(self.ent_coef),
+                             value_clip=0, advantage_normalization=0, loss_kind=LOSS_A2C)

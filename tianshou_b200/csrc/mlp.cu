@@ -528,6 +528,10 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
         // PPO surrogate of one row: objective value and d loss / d log_prob           (ppo.py:184-196)
         auto surrogate = [&](int r, float lp, float& obj) -> float {
             float Adv = rowv[r];
+            if (hp.loss_kind == TS_LOSS_A2C) {     // a2c.py:262-266: actor_loss = -(log_prob * adv).mean()
+                obj = lp * Adv;
+                return -inv_b * Adv;
+            }
             if (hp.advantage_normalization) Adv = (Adv - adv_mean) / (adv_std + adv_eps);
             const float ratio = expf(lp - rowv[2 * kRows + r]);
             const float rc = fminf(fmaxf(ratio, lo_c), hi_c);

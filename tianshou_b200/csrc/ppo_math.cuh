@@ -10,7 +10,7 @@ namespace ppo {
 
 struct Scalars {  // hyper-parameters narrowed to f32 where torch would narrow them
     float eps_clip, lo_c, hi_c, vf_coef, ent_coef, adv_eps, dual_clip, inv_b, adv_mean, adv_std;
-    int value_clip, adv_norm;
+    int value_clip, adv_norm, a2c;
 };
 
 __device__ __forceinline__ Scalars make_scalars(const ts_ppo_hparams& hp, int64_t global_rows,
@@ -25,6 +25,7 @@ __device__ __forceinline__ Scalars make_scalars(const ts_ppo_hparams& hp, int64_
     s.dual_clip = (float)hp.dual_clip;
     s.inv_b = 1.0f / (float)global_rows;
     s.value_clip = hp.value_clip;
+    s.a2c = hp.loss_kind == TS_LOSS_A2C;
     s.adv_norm = hp.advantage_normalization && adv_moments != nullptr;
     s.adv_mean = s.adv_norm ? adv_moments[0] : 0.0f;
     s.adv_std = s.adv_norm ? adv_moments[1] : 1.0f;
@@ -55,6 +56,11 @@ __device__ __forceinline__ void critic_row(const Scalars& s, float value, float 
 // clipped surrogate of one row: objective value and d(total loss)/d(logp)   (ppo.py:183-196)
 __device__ __forceinline__ void actor_row(const Scalars& s, float logp, float logp_old, float adv_raw, float& obj, float& gl) {
     float Adv = adv_raw;
+    if (s.a2c) {     // a2c.py:262-266: actor_loss = -(log_prob * adv).mean()
+        obj = logp * Adv;
+        gl = -s.inv_b * Adv;
+        return;
+    }
     if (s.adv_norm) Adv = (Adv - s.adv_mean) / (s.adv_std + s.adv_eps);
     const float ratio = expf(logp - logp_old);
     const float rc = fminf(fmaxf(ratio, s.lo_c), s.hi_c);
