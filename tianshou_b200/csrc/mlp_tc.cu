@@ -38,7 +38,8 @@ constexpr int kMaxAct = 16;
 constexpr int NO = 16;            // padded head width (N of the head GEMM, columns of dOut)
 
 // TMEM column map (fp32 accumulators)
-constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, cDH1 = 192, cDW2 = 256, cDW3 = 320, cDB2 = 336, cDB1 = 344, cDW1 = 352;
+// dW2 / dW1 carry one extra 8-column block: the bias gradient (B operand extended by a block of ones)
+constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, cDH1 = 192, cDW2 = 256 /* 72 */, cDW3 = 328 /* 16 */, cDW1 = 344 /* <= 40 */;
 // TS-mode A operand (bf16x3 pieces of the CURRENT activation / gradient tile: H1, then H2, then dZ2), 3 x 32 packed columns
 constexpr uint32_t cT = 384, kTPart = 32;
 constexpr uint32_t kTmemCols = 512;
@@ -140,16 +141,9 @@ __device__ __forceinline__ void gemm_ts(uint32_t tmem, uint32_t d_col, int N, co
 __device__ __forceinline__ void gemm_kx(uint32_t d_tmem, int M, int N, const Mat& A, int a_mn, const Mat& B, int b_mn, int K) {
     if (K == 16) gemm<1>(d_tmem, M, N, A, a_mn, B, b_mn); else gemm<2>(d_tmem, M, N, A, a_mn, B, b_mn);
 }
-// B = block of ones (one exact bf16 piece): D[64 x 8] = A^T 1 over the 128 rows, A used MN-major
-__device__ __forceinline__ void gemm_colsum(uint32_t d_tmem, const Mat& A, uint32_t ones_base, uint32_t ones_RS) {
-    umma::gemm_bf16x3_warp<kRows / 16, 3, 1>(d_tmem, A.base, A.part, A.RS, 128u, 2u * A.RS, ones_base, 0u, ones_RS, 128u,
-                                             2u * ones_RS, umma::idesc_bf16(64, 8, 1, 1));
-}
-
 struct Smem {   // byte offsets from the dynamic shared memory base (all multiples of 128)
     int KXP;
     Mat X, H1, H2, DO, W1, W2, W3;
-    uint32_t ONES, ONES_RS;
     uint32_t w3f, b1, b2, b3, ls, dof, rowv, red, act;
     uint32_t wblk, wblk_bytes;   // the "weight block" W1 | W2 | W3 | w3f | b1 | b2 | b3 | ls: one contiguous range, the unit
                                  // of the pre-split weight image in global memory (one bulk copy per network)
@@ -162,8 +156,10 @@ __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
     auto mat = [&](Mat& m, int rows, int cols) {
         m.base = sbase + o; m.part = mat_bytes(rows, cols); m.RS = (uint32_t)(cols / 8) * 128u; o += 3u * m.part;
     };
-    mat(s.X, kRows, s.KXP);
-    mat(s.H1, kRows, H);
+    // X and H1 carry one extra 8-column chunk of ones (piece 0 = 1.0, pieces 1, 2 = 0): as the B operand of the
+    // weight-gradient GEMMs it yields the bias gradient as 8 more accumulator columns instead of a GEMM of its own
+    mat(s.X, kRows, s.KXP + 8);
+    mat(s.H1, kRows, H + 8);
     mat(s.H2, kRows, H);
     mat(s.DO, kRows, NO);
     s.wblk = o;
@@ -176,7 +172,6 @@ __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
     s.b3 = o;   o += kMaxAct * 4;
     s.ls = o;   o += kMaxAct * 4;
     s.wblk_bytes = o - s.wblk;             // multiple of 128
-    s.ONES = sbase + o; s.ONES_RS = 128u; o += mat_bytes(kRows, 8);
     s.dof = o;  o += kRows * kMaxAct * 4;  // dOut in fp32 [r][a]
     s.act = o;  o += kRows * kMaxAct * 4;  // actions of the tile
     s.rowv = o; o += 4 * kRows * 4;        // adv, ret, logp_old, v_s
@@ -404,17 +399,17 @@ __device__ __forceinline__ void out_acc(float* p, float v, bool first) { *p = fi
 
 // Weight-gradient accumulators (TMEM, M = 64: row o = 16 q + lane for lane < 16) -> the CTA's partial
 // gradient row.  A lane owns a ROW of an accumulator, so direct stores would touch one 32-byte sector
-// per value (measured: 4-8 us per net).  The tile is transposed through shared memory instead (the H1
-// operand is dead after the last MMA; padded leading dimensions keep both sides bank-conflict free) and
+// per value (measured: 4-8 us per net).  The tile is transposed through shared memory instead (the H2
+// operand is dead by then; padded leading dimensions keep both sides bank-conflict free) and
 // written out with consecutive threads on consecutive addresses.
 constexpr int kLdW2 = H + 1, kLdW1 = 33, kScrW2 = 0, kScrW1 = kScrW2 + H * kLdW2, kScrW3 = kScrW1 + H * kLdW1,
               kScrB1 = kScrW3 + NO * kLdW2, kScrB2 = kScrB1 + H, kScrEnd = kScrB2 + H;
-static_assert(kScrEnd * 4 <= 3 * kRows * H * 2, "gradient scratch must fit in the H1 operand");
+static_assert(kScrEnd * 4 <= 3 * kRows * H * 2, "gradient scratch must fit in the H2 operand");
 __device__ __forceinline__ void grad_out(uint8_t* sm0, const Smem& S, uint32_t tmem, const NetG& g, int obs_dim, int out_dim,
                                          float* __restrict__ grad, bool first) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cq = warp >> 2;
-    float* scr = reinterpret_cast<float*>(sm0 + S.H1.base);
+    float* scr = reinterpret_cast<float*>(sm0 + S.H2.base);       // H2 (dZ2) is dead after the dW2 / dH1 stage
     const uint32_t t0 = tmem + ((32u * q) << 16);
     const int o = 16 * q + lane;
     float v[8];
@@ -440,7 +435,7 @@ __device__ __forceinline__ void grad_out(uint8_t* sm0, const Smem& S, uint32_t t
             for (int j = 0; j < 8; ++j) scr[kScrW3 + (8 * cq + j) * kLdW2 + o] = v[j];
         }
     } else {                                               // db2 (cq == 2), db1 (cq == 3): column 0 of the ones-GEMM
-        umma::tmem_ld8(t0 + (cq == 2 ? cDB2 : cDB1), v);
+        umma::tmem_ld8(t0 + (cq == 2 ? cDW2 + (uint32_t)H : cDW1 + (uint32_t)S.KXP), v);
         if (lane < 16) scr[(cq == 2 ? kScrB2 : kScrB1) + o] = v[0];
     }
     __syncthreads();
@@ -501,8 +496,7 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
     epi_head_input_grad(sm, sm0, S, tmem, out_dim, h2);
     tstamp(17);                                     // H2 := dZ2
     pipe.run([&] {
-        gemm<kRows / 16>(tmem + cDW2, 64, H, S.H2, 1, S.H1, 1);                       // dW2 = dZ2^T H1
-        gemm_colsum(tmem + cDB2, S.H2, S.ONES, S.ONES_RS);                            // db2 = dZ2^T 1
+        gemm<kRows / 16>(tmem + cDW2, 64, H + 8, S.H2, 1, S.H1, 1);                   // [dW2 | db2] = dZ2^T [H1 | 1]
         gemm_ts(tmem, cDH1, H, S.W2, 1);                                              // dH1 = dZ2 W2, A = dZ2 from TMEM
     });
     tstamp(18);
@@ -510,8 +504,7 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
     epi_dtanh(sm0, S.H1, tmem, cDH1, h1);                                             // H1 := dZ1
     tstamp(19);
     pipe.run([&] {
-        gemm<kRows / 16>(tmem + cDW1, 64, S.KXP, S.H1, 1, S.X, 1);                    // dW1 = dZ1^T X
-        gemm_colsum(tmem + cDB1, S.H1, S.ONES, S.ONES_RS);                            // db1 = dZ1^T 1
+        gemm<kRows / 16>(tmem + cDW1, 64, S.KXP + 8, S.H1, 1, S.X, 1);                // [dW1 | db1] = dZ1^T [X | 1]
     });
     tstamp(20);
     grad_out(sm0, S, tmem, g, obs_dim, out_dim, grad, first);
@@ -619,9 +612,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
 
     if (warp == 0) umma::tmem_alloc(&s_tmem, kTmemCols);
     if (tid == 0) { umma::mbar_init(&s_bar, 1); umma::mbar_init(&s_wbar, 1); umma::fence_mbar_init(); }
-    {   // block of ones (bf16 1.0 = 0x3F80), blocked layout with 1 chunk per row
-        uint32_t* ones = reinterpret_cast<uint32_t*>(sm0 + S.ONES);
-        for (int e = tid; e < kRows * 8 / 2; e += kThreads) ones[e] = 0x3F803F80u;
+    for (int e = tid; e < 2 * 3 * kRows; e += kThreads) {   // the ones chunks of X and H1 (bf16 1.0 = 0x3F80 in piece 0)
+        const int r = e % kRows, pc = (e / kRows) % 3;
+        const Mat& M = e < 3 * kRows ? S.X : S.H1;
+        const uint32_t c = e < 3 * kRows ? (uint32_t)S.KXP : (uint32_t)H;
+        const uint32_t w = pc == 0 ? 0x3F803F80u : 0u;
+        *reinterpret_cast<uint4*>(sm0 + (M.base + pc * M.part + moff((uint32_t)r, c, M.RS))) = make_uint4(w, w, w, w);
     }
     umma::fence_before_sync();
     __syncthreads();
