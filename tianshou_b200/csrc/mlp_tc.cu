@@ -172,7 +172,7 @@ __host__ __device__ inline Smem make_smem(int obs_dim, uint32_t sbase) {
     s.b3 = o;   o += kMaxAct * 4;
     s.ls = o;   o += kMaxAct * 4;
     s.wblk_bytes = o - s.wblk;             // multiple of 128
-    s.dof = o;  o += kRows * kMaxAct * 4;  // dOut in fp32 [r][a]
+    s.dof = o;  o += kRows * kMaxAct * 4;  // dOut in fp32 [a][r] (rows on consecutive banks)
     s.act = o;  o += kRows * kMaxAct * 4;  // actions of the tile
     s.rowv = o; o += 4 * kRows * 4;        // adv, ret, logp_old, v_s
     s.red = o;  o += 256 * 4;              // [0,12) per-warp sums, [64,80) 1/var, [80,96) log sigma + log sqrt(2 pi),
@@ -320,7 +320,7 @@ struct Pipe {   // MMA issue / completion handshake
     // all threads: make smem writes + tcgen05.ld's visible; then WARP 0 (all lanes, warp-uniform
     // control flow) runs `f`, whose MMAs are issued by one elected lane, and commits.
     template <class F>
-    __device__ __forceinline__ void run(F&& f) {
+    __device__ __forceinline__ void issue(F&& f) {
         umma::tmem_wait_st();
         umma::fence_async_smem();
         umma::fence_before_sync();
@@ -332,10 +332,16 @@ struct Pipe {   // MMA issue / completion handshake
             if (umma::elect_one()) umma::mma_commit(bar);
             __syncwarp();
         }
+    }
+    // all threads: the MMAs of the last issue() have completed (work that does not touch their operands or
+    // accumulators may run between issue() and wait())
+    __device__ __forceinline__ void wait() {
         umma::mbar_wait(bar, phase);
         phase ^= 1u;
         umma::fence_after_sync();
     }
+    template <class F>
+    __device__ __forceinline__ void run(F&& f) { issue(f); wait(); }
 };
 
 // Epilogue thread map: warp w -> TMEM sub-partition q = w & 3 (rows 32q + lane), column group
@@ -362,18 +368,18 @@ __device__ __forceinline__ void epi_dtanh(uint8_t* sm0, const Mat& ACT, uint32_t
     store_chunk8(sm0, ACT, r, c0, v);
     store_chunk8(sm0, ACT, r, c0 + 8, v + 8);
 }
-// dZ2 = (dOut W3) * (1 - H2^2) written over H2 (K = out_dim is tiny: SIMT)
-__device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t tmem, int out_dim,
-                                                    const float (&h)[kCols]) {
+// dZ2 = (dOut W3) * (1 - H2^2) (K = out_dim is tiny: SIMT).  Split in two so that the arithmetic overlaps the dW3 MMA
+// that is still reading H2: compute into registers, then (after the MMA completed) store over H2 and into TMEM.
+__device__ __forceinline__ void head_input_grad_compute(uint8_t* sm, const Smem& S, int out_dim, const float (&h)[kCols],
+                                                        float (&acc)[kCols]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
-    const float* dof = reinterpret_cast<const float*>(sm + S.dof) + r * kMaxAct;
+    const float* dof = reinterpret_cast<const float*>(sm + S.dof) + r;
     const float* w3f = reinterpret_cast<const float*>(sm + S.w3f);
-    float acc[kCols];
 #pragma unroll
     for (int j = 0; j < kCols; ++j) acc[j] = 0.0f;
     for (int a = 0; a < out_dim; ++a) {
-        const float dv = dof[a];
+        const float dv = dof[a * kRows];
 #pragma unroll
         for (int j = 0; j < kCols; j += 4) {
             const float4 w = *reinterpret_cast<const float4*>(w3f + a * H + c0 + j);
@@ -383,13 +389,17 @@ __device__ __forceinline__ void epi_head_input_grad(uint8_t* sm, uint8_t* sm0, c
     }
 #pragma unroll
     for (int j = 0; j < kCols; ++j) acc[j] = acc[j] * fmaf(-h[j], h[j], 1.0f);
+}
+__device__ __forceinline__ void head_input_grad_store(uint8_t* sm0, const Smem& S, uint32_t tmem, const float (&acc)[kCols]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r = 32u * (warp & 3) + lane, c0 = (uint32_t)kCols * (warp >> 2);
     store_row16(sm0, S.H2, r, c0, acc, tmem + ((32u * (warp & 3)) << 16) + cT);
 }
 // write one row of dOut: fp32 side copy + bf16x3 operand (columns >= out_dim are zero)
 __device__ __forceinline__ void write_dout_row(uint8_t* sm, uint8_t* sm0, const Smem& S, uint32_t r, const float* dv) {
-    float* dof = reinterpret_cast<float*>(sm + S.dof) + r * kMaxAct;
+    float* dof = reinterpret_cast<float*>(sm + S.dof) + r;
 #pragma unroll
-    for (int a = 0; a < kMaxAct; ++a) dof[a] = dv[a];
+    for (int a = 0; a < kMaxAct; ++a) dof[a * kRows] = dv[a];
     store_chunk8(sm0, S.DO, r, 0, dv);
     store_chunk8(sm0, S.DO, r, 8, dv + 8);
 }
@@ -405,6 +415,8 @@ __device__ __forceinline__ void out_acc(float* p, float v, bool first) { *p = fi
 constexpr int kLdW2 = H + 1, kLdW1 = 33, kScrW2 = 0, kScrW1 = kScrW2 + H * kLdW2, kScrW3 = kScrW1 + H * kLdW1,
               kScrB1 = kScrW3 + NO * kLdW2, kScrB2 = kScrB1 + H, kScrEnd = kScrB2 + H;
 static_assert(kScrEnd * 4 <= 3 * kRows * H * 2, "gradient scratch must fit in the H2 operand");
+// PART 0: dW2, db2, dW3 (complete after the dW2 / dH1 stage: runs while the dW1 MMA is in flight); PART 1: dW1, db1.
+template <int PART>
 __device__ __forceinline__ void grad_out(uint8_t* sm0, const Smem& S, uint32_t tmem, const NetG& g, int obs_dim, int out_dim,
                                          float* __restrict__ grad, bool first) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -413,48 +425,56 @@ __device__ __forceinline__ void grad_out(uint8_t* sm0, const Smem& S, uint32_t t
     const uint32_t t0 = tmem + ((32u * q) << 16);
     const int o = 16 * q + lane;
     float v[8];
+    if (PART == 0) {
 #pragma unroll
-    for (int c0 = 0; c0 < H; c0 += 32) {                  // dW2 [o][i]
-        umma::tmem_ld8(t0 + cDW2 + c0 + 8 * cq, v);
-        if (lane < 16) {
+        for (int c0 = 0; c0 < H; c0 += 32) {                  // dW2 [o][i]
+            umma::tmem_ld8(t0 + cDW2 + c0 + 8 * cq, v);
+            if (lane < 16) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) scr[kScrW2 + o * kLdW2 + c0 + 8 * cq + j] = v[j];
+                for (int j = 0; j < 8; ++j) scr[kScrW2 + o * kLdW2 + c0 + 8 * cq + j] = v[j];
+            }
         }
-    }
-    if (8 * cq < S.KXP) {                                  // dW1 [o][i]   (warp-uniform)
-        umma::tmem_ld8(t0 + cDW1 + 8 * cq, v);
-        if (lane < 16) {
+        if (cq < NO / 8) {                                     // dW3^T [k][a] -> [a][k]
+            umma::tmem_ld8(t0 + cDW3 + 8 * cq, v);
+            if (lane < 16) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) scr[kScrW1 + o * kLdW1 + 8 * cq + j] = v[j];
+                for (int j = 0; j < 8; ++j) scr[kScrW3 + (8 * cq + j) * kLdW2 + o] = v[j];
+            }
+        } else if (cq == 2) {                                  // db2: the ones column of [dW2 | db2]
+            umma::tmem_ld8(t0 + cDW2 + (uint32_t)H, v);
+            if (lane < 16) scr[kScrB2 + o] = v[0];
         }
-    }
-    if (cq < NO / 8) {                                     // dW3^T [k][a] -> [a][k]
-        umma::tmem_ld8(t0 + cDW3 + 8 * cq, v);
-        if (lane < 16) {
+        __syncthreads();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) scr[kScrW3 + (8 * cq + j) * kLdW2 + o] = v[j];
+        for (int u = 0; u < H * H / kThreads; ++u) {
+            const int e = tid + u * kThreads;
+            out_acc(grad + g.w2 + e, scr[kScrW2 + (e >> 6) * kLdW2 + (e & (H - 1))], first);
         }
-    } else {                                               // db2 (cq == 2), db1 (cq == 3): column 0 of the ones-GEMM
-        umma::tmem_ld8(t0 + (cq == 2 ? cDW2 + (uint32_t)H : cDW1 + (uint32_t)S.KXP), v);
-        if (lane < 16) scr[(cq == 2 ? kScrB2 : kScrB1) + o] = v[0];
-    }
-    __syncthreads();
+        if (warp < out_dim) {
+            out_acc(grad + g.w3 + warp * H + lane, scr[kScrW3 + warp * kLdW2 + lane], first);
+            out_acc(grad + g.w3 + warp * H + 32 + lane, scr[kScrW3 + warp * kLdW2 + 32 + lane], first);
+        }
+        if (tid < H) out_acc(grad + g.b2 + tid, scr[kScrB2 + tid], first);
+    } else {
+        if (8 * cq < S.KXP) {                                  // dW1 [o][i]   (warp-uniform)
+            umma::tmem_ld8(t0 + cDW1 + 8 * cq, v);
+            if (lane < 16) {
 #pragma unroll
-    for (int u = 0; u < H * H / kThreads; ++u) {
-        const int e = tid + u * kThreads;
-        out_acc(grad + g.w2 + e, scr[kScrW2 + (e >> 6) * kLdW2 + (e & (H - 1))], first);
-    }
-    if (lane < obs_dim) {
+                for (int j = 0; j < 8; ++j) scr[kScrW1 + o * kLdW1 + 8 * cq + j] = v[j];
+            }
+        }
+        if (cq == 3) {                                         // db1: the ones column of [dW1 | db1]
+            umma::tmem_ld8(t0 + cDW1 + (uint32_t)S.KXP, v);
+            if (lane < 16) scr[kScrB1 + o] = v[0];
+        }
+        __syncthreads();
+        if (lane < obs_dim) {
 #pragma unroll
-        for (int r = warp; r < H; r += kThreads / 32)
-            out_acc(grad + g.w1 + (int64_t)r * obs_dim + lane, scr[kScrW1 + r * kLdW1 + lane], first);
+            for (int r = warp; r < H; r += kThreads / 32)
+                out_acc(grad + g.w1 + (int64_t)r * obs_dim + lane, scr[kScrW1 + r * kLdW1 + lane], first);
+        }
+        if (tid < H) out_acc(grad + g.b1 + tid, scr[kScrB1 + tid], first);
     }
-    if (warp < out_dim) {
-        out_acc(grad + g.w3 + warp * H + lane, scr[kScrW3 + warp * kLdW2 + lane], first);
-        out_acc(grad + g.w3 + warp * H + 32 + lane, scr[kScrW3 + warp * kLdW2 + 32 + lane], first);
-    }
-    if (tid < H) out_acc(grad + g.b1 + tid, scr[kScrB1 + tid], first);
-    else if (tid < 2 * H) out_acc(grad + g.b2 + tid - H, scr[kScrB2 + tid - H], first);
 }
 
 // Sum 32 per-lane values over the warp with 31 shuffles; lane j returns the total of v[j].
@@ -491,10 +511,13 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
                                                const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad,
                                                const float (&h1)[kCols], const float (&h2)[kCols], bool first,
                                                F&& weights_dead) {
-    pipe.run([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });      // dW3^T = H2^T dOut
+    pipe.issue([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });    // dW3^T = H2^T dOut
+    float dz2[kCols];
+    head_input_grad_compute(sm, S, out_dim, h2, dz2);          // overlaps the MMA (reads dof / w3f / registers only)
+    pipe.wait();
     tstamp(16);
-    epi_head_input_grad(sm, sm0, S, tmem, out_dim, h2);
-    tstamp(17);                                     // H2 := dZ2
+    head_input_grad_store(sm0, S, tmem, dz2);                  // H2 := dZ2 (the MMA no longer reads H2), T := dZ2
+    tstamp(17);
     pipe.run([&] {
         gemm<kRows / 16>(tmem + cDW2, 64, H + 8, S.H2, 1, S.H1, 1);                   // [dW2 | db2] = dZ2^T [H1 | 1]
         gemm_ts(tmem, cDH1, H, S.W2, 1);                                              // dH1 = dZ2 W2, A = dZ2 from TMEM
@@ -503,11 +526,13 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
     weights_dead();
     epi_dtanh(sm0, S.H1, tmem, cDH1, h1);                                             // H1 := dZ1
     tstamp(19);
-    pipe.run([&] {
+    pipe.issue([&] {
         gemm<kRows / 16>(tmem + cDW1, 64, S.KXP + 8, S.H1, 1, S.X, 1);                // [dW1 | db1] = dZ1^T [X | 1]
     });
+    grad_out<0>(sm0, S, tmem, g, obs_dim, out_dim, grad, first);     // dW2 / db2 / dW3 leave while the MMA runs
+    pipe.wait();
     tstamp(20);
-    grad_out(sm0, S, tmem, g, obs_dim, out_dim, grad, first);
+    grad_out<1>(sm0, S, tmem, g, obs_dim, out_dim, grad, first);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
