@@ -48,6 +48,23 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
     def _loss_hparams(self) -> Any:
         raise NotImplementedError
 
+    def update(self, buffer: ReplayBuffer, batch_size: int | None, repeat: int) -> A2CTrainingStats:
+        """``OnPolicyAlgorithm.update`` (algorithm_base.py:854-865).  With the default reference-exact minibatch order
+        the ``repeat`` permutation draws of ``Batch.split`` (batch.py:1209) are started here, in the background, so that
+        they overlap the upload / value pass / GAE that precede the first pass (nothing in between touches numpy's
+        global stream: ``sample(0)`` draws nothing)."""
+        job = None
+        if (self.minibatch_shuffle == "numpy" and buffer is not None and self.policy.is_within_training_step
+                and len(buffer) > 0 and repeat > 0 and torch.cuda.is_available()):
+            job = NumpyGlobalPermutationJob(self._host_perm_rows(repeat, len(buffer)), repeat)
+        self._perm_job = job
+        try:
+            return super().update(buffer=buffer, batch_size=batch_size, repeat=repeat)
+        finally:
+            self._perm_job = None
+            if job is not None:
+                job.__exit__(None, None, None)      # joins the threads, writes the advanced state back into numpy
+
     def _one_pass(self, batch: Batch, perm_r: torch.Tensor, bounds: list[tuple[int, int]], hp: Any, stats: torch.Tensor,
                   r: int, rank: int, wsize: int) -> None:
         """Pass r over the minibatches in the order ``perm_r`` (optional advantage recompute first, ppo.py:174-178)."""
@@ -94,10 +111,14 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
             # the reference's RNG draws (np.random.permutation on the global stream once per pass, batch.py:1209),
             # bit-identical, produced ahead of the passes by background threads straight into pinned memory (one row per
             # pass, so a pending async copy is never overwritten) and overlapped with the GPU work enqueued so far
-            with NumpyGlobalPermutationJob(self._host_perm_rows(repeat, N), repeat) as job:
+            job = getattr(self, "_perm_job", None)
+            if job is not None and job.shape == (repeat, N):       # started by update(), already running
                 for r in range(repeat):
-                    perm_r = job.wait(r).to(dev, non_blocking=True)
-                    self._one_pass(batch, perm_r, bounds, hp, stats[r * n_mb:], r, rank, wsize)
+                    self._one_pass(batch, job.wait(r).to(dev, non_blocking=True), bounds, hp, stats[r * n_mb:], r, rank, wsize)
+            else:                                                    # _update_with_batch called directly
+                with NumpyGlobalPermutationJob(self._host_perm_rows(repeat, N), repeat) as job:
+                    for r in range(repeat):
+                        self._one_pass(batch, job.wait(r).to(dev, non_blocking=True), bounds, hp, stats[r * n_mb:], r, rank, wsize)
         result = self._stats_from_device(stats)   # the only host sync of the update
         self._rms_end()
         self._flat.export_state(self.optim._optim)

@@ -52,26 +52,30 @@ struct PermJob {
             int p = pos;
             // One iteration per DRAW (not per position): write the candidate, step to the next position only when it
             // is accepted (v <= i).  No data-dependent branch -- random_interval's rejection loop mispredicts ~30 % of
-            // the time when written as do/while.  mask = smallest 2^k - 1 >= i.
+            // the time when written as do/while.  The generator block is tempered in a separate (vectorisable) loop.
             uint32_t* jd = j.data();
+            uint32_t tmp[kMtN];
             int64_t i = n - 1;
             while (i >= 1) {
-                // positions i in (lower, mask] share one mask: the loop-carried chain is just compare + subtract
-                const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
-                const int64_t lower = (int64_t)(mask >> 1);
-                while (i > lower) {
-                    if (p == kMtN) { mt_gen(key); p = 0; }
-                    const int avail = kMtN - p;
-                    int d = 0;
+                if (p == kMtN) { mt_gen(key); p = 0; }
+                const int avail = kMtN - p;
+                for (int d = 0; d < avail; ++d) {
+                    uint32_t y = key[p + d];
+                    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+                    tmp[d] = y;
+                }
+                int d = 0;
+                while (d < avail && i >= 1) {
+                    // positions i in (lower, mask] share one mask: the loop-carried chain is just compare + subtract
+                    const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
+                    const int64_t lower = (int64_t)(mask >> 1);
                     for (; d < avail && i > lower; ++d) {
-                        uint32_t y = key[p + d];
-                        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-                        const uint32_t v = y & mask;
+                        const uint32_t v = tmp[d] & mask;
                         jd[i] = v;
                         i -= (int64_t)(v <= (uint32_t)i);
                     }
-                    p += d;
                 }
+                p += d;
             }
             pos = p;
             { std::lock_guard<std::mutex> lk(mu); state[r] = 1; }

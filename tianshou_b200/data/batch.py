@@ -744,6 +744,7 @@ class NumpyGlobalPermutationJob:
         from .._cabi import call
         assert rows.dtype == torch.int32 and not rows.is_cuda and rows.is_contiguous() and rows.shape[0] >= repeat
         self._rows, self._repeat, self._n = rows, repeat, rows.shape[1]
+        self.shape = (repeat, self._n)
         self._st = np.random.get_state()
         self._job = None
         if self._st[0] != "MT19937":          # not the legacy MT19937 state: plain numpy draws, in order, up front
