@@ -44,9 +44,15 @@ struct PermJob {
     std::thread producer;
     std::vector<std::thread> workers;
     std::atomic<int> next_apply{0};
+    int applied = 0;                             // passes completely applied (guarded by mu)
+    static constexpr int kAhead = 6;             // the producer stays at most this many passes ahead of the workers
 
     void produce() {
         for (int r = 0; r < repeat; ++r) {
+            {   // back-pressure: bounded memory (4 n bytes per pass in flight) whatever `repeat` is
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return r - applied < kAhead; });
+            }
             std::vector<uint32_t>& j = js[r];
             j.resize((size_t)(n > 0 ? n : 1));
             int p = pos;
@@ -92,7 +98,7 @@ struct PermJob {
             const std::vector<uint32_t>& j = js[r];
             for (int64_t i = n - 1; i >= 1; --i) { const uint32_t v = j[(size_t)i]; const int32_t t = o[v]; o[v] = o[i]; o[i] = t; }
             std::vector<uint32_t>().swap(js[r]);
-            { std::lock_guard<std::mutex> lk(mu); state[r] = 2; }
+            { std::lock_guard<std::mutex> lk(mu); state[r] = 2; ++applied; }
             cv.notify_all();
         }
     }
