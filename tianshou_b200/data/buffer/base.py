@@ -301,7 +301,13 @@ class ReplayBuffer:
         """Vectorised ``_update_state_pre_add`` (buffer_base.py:360-418) for sub-buffers ``ids``
         (each at most once).  Returns absolute (insertion idx, ep_return, ep_len, ep_start idx)."""
         ids = np.asarray(ids, dtype=np.int64)
-        if len(np.unique(ids)) != len(ids):  # same sub-buffer twice: order matters, go one by one
+        # duplicate check without a sort: strictly increasing ids (the Collector's ready_env_ids / arange) are unique
+        unique = len(ids) <= 1 or bool(np.all(ids[1:] > ids[:-1]))
+        if not unique:
+            seen = np.zeros(len(self._cap), dtype=bool)
+            seen[ids] = True
+            unique = int(seen.sum()) == len(ids)
+        if not unique:  # same sub-buffer twice: order matters, go one by one
             parts = [self._advance(ids[k:k + 1], rew[k:k + 1], done[k:k + 1]) for k in range(len(ids))]
             return tuple(np.concatenate(p) for p in zip(*parts, strict=True))  # type: ignore[return-value]
         off, cap = self._offset[ids], self._cap[ids]
@@ -597,15 +603,22 @@ class ReplayBufferManager(ReplayBuffer):
         ids = np.asarray(buffer_ids, dtype=np.int64)
         idx, ep_ret, ep_len, ep_start = self._advance(
             ids, np.asarray(batch.rew, dtype=np.float64)[: len(ids)], np.asarray(batch.done)[: len(ids)])
+        # lock-step rollouts write an arithmetic progression of slots (env e at e * cap + t): a strided slice
+        # assignment instead of a fancy-indexed one (one strided memcpy per key instead of E small ones)
+        where: Any = idx
+        if len(idx) > 1:
+            step = int(idx[1] - idx[0])
+            if step > 0 and bool(np.all(idx[1:] - idx[:-1] == step)):
+                where = slice(int(idx[0]), int(idx[-1]) + 1, step)
         try:
-            self._meta[idx] = batch
+            self._meta[where] = batch
         except ValueError:
             batch.rew = batch.rew.astype(float)
             batch.done = batch.done.astype(bool)
             batch.terminated = batch.terminated.astype(bool)
             batch.truncated = batch.truncated.astype(bool)
             self._allocate(batch, stack=False)
-            self._meta[idx] = batch
+            self._meta[where] = batch
         self._mirror_add(idx, batch)
         return idx, ep_ret, ep_len, ep_start
 
