@@ -196,3 +196,26 @@ def test_permutation_job_matches_numpy_stream():
                 job.wait(r)
         assert np.array_equal(rows.numpy(), ref), (seed, n)
         assert np.array_equal(np.random.rand(3), ref_next)
+
+
+def test_vector_buffer_add_slice_path_equals_fancy_path():
+    """Lock-step adds (ids = arange) take the strided-slice write; any other id order takes the fancy-indexed write.
+    Same buffer contents, same returned (index, ep_return, ep_len, ep_start) rows (manager.py:131-198)."""
+    from tianshou_b200.data import Batch, VectorReplayBuffer
+    rng = np.random.default_rng(1)
+    E, cap = 12, 5
+    a, b = VectorReplayBuffer(E * cap, E), VectorReplayBuffer(E * cap, E)
+    for _ in range(13):                                 # wraps every sub-buffer twice
+        s = Batch(obs=rng.standard_normal((E, 3)).astype(np.float32), act=rng.integers(0, 2, E), rew=rng.standard_normal(E),
+                  terminated=rng.random(E) < 0.2, truncated=np.zeros(E, bool),
+                  obs_next=rng.standard_normal((E, 3)).astype(np.float32), info=Batch())
+        ra = a.add(s, buffer_ids=np.arange(E))
+        perm = rng.permutation(E)
+        sb = Batch(obs=s.obs[perm], act=s.act[perm], rew=s.rew[perm], terminated=s.terminated[perm],
+                   truncated=s.truncated[perm], obs_next=s.obs_next[perm], info=Batch())
+        rb = b.add(sb, buffer_ids=perm)
+        for x, y in zip(ra, rb, strict=True):
+            assert np.array_equal(np.asarray(x)[perm], np.asarray(y))
+    for k in ("obs", "act", "rew", "terminated", "truncated", "done", "obs_next"):
+        assert np.array_equal(np.asarray(a._meta[k]), np.asarray(b._meta[k])), k
+    assert np.array_equal(a.last_index, b.last_index) and len(a) == len(b)
