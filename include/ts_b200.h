@@ -119,11 +119,14 @@ int ts_unfinished_index(const int64_t* offset, int64_t E, const uint8_t* done,
                         const int64_t* last_index, const int64_t* lengths, int64_t* out,
                         int64_t* count_out, ts_stream_t stream);
 /* sample_indices(0): all valid slots, sub-buffer-major, chronological inside each sub-buffer
- * (manager.py:217-234, buffer_base.py:519-525).  seg_start: device int64[E+1] scratch that
- * receives the exclusive prefix sum of lengths; out capacity >= sum(lengths); total_out int64[1]. */
+ * (manager.py:217-234, buffer_base.py:519-525).  insertion_idx: device int64[E], every sub-buffer's
+ * `_insertion_idx` relative to its own start (nullable: derived as last_index + 1, which is only right for
+ * buffers filled by add() alone -- from_data() / dropnull() move it independently).  seg_start: device
+ * int64[E+1] scratch that receives the exclusive prefix sum of lengths; out capacity >= sum(lengths);
+ * total_out int64[1]. */
 int ts_sample_all_indices(const int64_t* offset, int64_t E, const int64_t* last_index,
-                          const int64_t* lengths, int64_t* seg_start, int64_t* out,
-                          int64_t out_capacity, int64_t* total_out, ts_stream_t stream);
+                          const int64_t* lengths, const int64_t* insertion_idx, int64_t* seg_start,
+                          int64_t* out, int64_t out_capacity, int64_t* total_out, ts_stream_t stream);
 /* mark[p] = 1 if idx[p] is in `members` (np.isin, algorithm_base.py:715).  table: device u8
  * scratch of table_size >= max slot + 1, left zeroed on return. */
 int ts_mark_members(const int64_t* idx, int64_t n, const int64_t* members,

@@ -559,9 +559,43 @@ def gen_a2c():
     print("a2c_ref.npz", len(out), "arrays; gradient_steps", int(out["u0_gradient_steps"]))
 
 
+def gen_fromdata():
+    """sample_indices(0) / prev / next / unfinished_index on buffers whose insertion index was NOT produced by add():
+    ``ReplayBuffer.from_data`` (buffer_base.py:382-418: size = N, _insertion_idx stays 0, last_index stays 0), then a few
+    ``add`` calls on top (wrap-around from slot 0)."""
+    from tianshou.data import ReplayBuffer as RefRB
+    rng = np.random.default_rng(99)
+    out = {}
+    for case, (n, extra) in enumerate([(7, 0), (7, 3), (12, 12), (5, 7)]):
+        obs = rng.standard_normal((n, 2)).astype(np.float32)
+        act = rng.standard_normal((n, 1)).astype(np.float32)
+        rew = rng.standard_normal(n)
+        term = rng.random(n) < 0.2
+        trunc = (rng.random(n) < 0.1) & ~term
+        obs_next = rng.standard_normal((n, 2)).astype(np.float32)
+        buf = RefRB.from_data(obs, act, rew, term, trunc, term | trunc, obs_next)
+        p = f"fd{case}_"
+        out.update({p + "obs": obs, p + "act": act, p + "rew": rew, p + "terminated": term, p + "truncated": trunc,
+                    p + "obs_next": obs_next, p + "extra": extra})
+        for j in range(extra):
+            b = Batch(obs=rng.standard_normal(2).astype(np.float32), act=rng.standard_normal(1).astype(np.float32),
+                      rew=float(rng.standard_normal()), terminated=bool(rng.random() < 0.2), truncated=False,
+                      obs_next=rng.standard_normal(2).astype(np.float32))
+            for k in ("obs", "act", "rew", "terminated", "truncated", "obs_next"):
+                out[p + f"add{j}_" + k] = np.asarray(b[k])
+            buf.add(b)
+        q = np.arange(-2, n + 2)
+        out.update({p + "all": buf.sample_indices(0), p + "query": q, p + "prev": buf.prev(q % n), p + "next": buf.next(q % n),
+                    p + "unfinished": buf.unfinished_index(), p + "len": len(buf), p + "last_index": np.asarray(buf.last_index),
+                    p + "done": np.asarray(buf.done, dtype=bool)})
+    out["n_cases"] = 4
+    np.savez_compressed(os.path.join(OUT, "fromdata_ref.npz"), **out)
+    print("fromdata_ref.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["returns", "index", "segtree", "ppo", "ppo_discrete", "a2c"]
+    which = sys.argv[1:] or ["returns", "index", "segtree", "ppo", "ppo_discrete", "a2c", "fromdata"]
     for w in which:
         {"returns": gen_returns, "index": gen_index, "segtree": gen_segtree, "ppo": gen_ppo,
-         "ppo_discrete": gen_ppo_discrete, "a2c": gen_a2c}[w]()
+         "ppo_discrete": gen_ppo_discrete, "a2c": gen_a2c, "fromdata": gen_fromdata}[w]()

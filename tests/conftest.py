@@ -35,3 +35,24 @@ def load_golden(name: str):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Dump the observed parity errors recorded by the tests (ts_testutil.record_parity)."""
+    try:
+        import json
+
+        import ts_testutil
+        if not ts_testutil.PARITY:
+            return
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out_dir, exist_ok=True)
+        path = os.path.join(out_dir, "parity_report.json")
+        merged = {}
+        if os.path.exists(path) and os.environ.get("TS_PARITY_APPEND", "0") == "1":
+            merged = json.load(open(path))
+        merged.update(ts_testutil.PARITY)
+        with open(path, "w") as f:
+            json.dump(merged, f, indent=1, sort_keys=True)
+    except Exception as e:  # never turn a green run red because of the report
+        sys.stderr.write(f"parity report not written: {e}\n")

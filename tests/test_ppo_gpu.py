@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import oracle_np as onp
-from ts_testutil import PARAM_ORDER, build_ppo, load_golden, named_params, restore_vector_buffer, synth_rollout
+from ts_testutil import PARAM_ORDER, build_ppo, load_golden, named_params, record_parity, restore_vector_buffer, synth_rollout
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -144,20 +144,27 @@ def test_ppo_update_matches_reference(variant):
             stats = algo.update(buffer=buf, batch_size=bs, repeat=repeat)
         assert np.array_equal(captured["indices"], g[o + "indices"])                  # sample(0) order, bit-exact
         pre = captured["pre"]
-        np.testing.assert_allclose(pre["v_s"], g[o + "v_s"], rtol=2e-5, atol=5e-6)
-        assert np.allclose(pre["returns"], g[o + "returns"], rtol=1e-4, atol=2e-5)
-        assert np.allclose(pre["adv"], g[o + "adv"], rtol=1e-4, atol=2e-5)
-        np.testing.assert_allclose(pre["logp_old"], g[o + "logp_old"], rtol=2e-5, atol=2e-5)
+        # North star: returns / advantages within 1e-5 relative of the reference's fp32 results.  Tolerance used here:
+        # |err| <= 1e-5 * |ref| + 1e-5 * max|ref|  (elementwise relative + an absolute floor scaled to the column, because
+        # advantages cross zero); observed errors are recorded in gpurun_out/parity_report.json.
+        tag = f"ppo_{variant}_u{u}"
+        for k in ("v_s", "returns", "adv", "logp_old"):
+            ref = g[o + k]
+            record_parity(f"{tag}/{k}", pre[k], ref, rtol=1e-5, atol=1e-5 * float(np.abs(ref).max()))
         assert stats.gradient_steps == int(g[o + "gradient_steps"])
-        ref_losses = g[o + "losses"]
+        ref_losses = g[o + "losses"]                       # [steps, 4]: what ppo.py:213-216 appended per optimiser step
+        table = algo.last_loss_table
+        assert table.shape[0] == ref_losses.shape[0]
         for col, name in enumerate(["loss", "actor_loss", "vf_loss", "ent_loss"]):
+            # per-minibatch, row by row (not only mean / min / max)
+            record_parity(f"{tag}/per_step_{name}", table[:, col], ref_losses[:, col], rtol=2e-4,
+                          atol=2e-5 * max(1e-3, float(np.abs(ref_losses[:, col]).max())))
             s = getattr(stats, name)
-            np.testing.assert_allclose(s.mean, ref_losses[:, col].mean(), rtol=5e-4, atol=2e-5, err_msg=name)
-            np.testing.assert_allclose(s.max, ref_losses[:, col].max(), rtol=5e-4, atol=5e-5, err_msg=name)
-            np.testing.assert_allclose(s.min, ref_losses[:, col].min(), rtol=5e-4, atol=5e-5, err_msg=name)
+            np.testing.assert_allclose(s.mean, ref_losses[:, col].mean(), rtol=2e-4, atol=2e-5, err_msg=name)
         for k, pv in named_params(actor, critic).items():
-            np.testing.assert_allclose(pv.detach().cpu().numpy(), g[o + "p_" + k], rtol=2e-3, atol=3e-5,
-                                       err_msg=f"{variant} update {u} param {k}")
+            # Adam divides by sqrt(v): at step t a gradient difference of relative size e moves the parameter by up to
+            # ~lr * e / (1 - beta1) -- the absolute term is stated in units of one Adam step (lr)
+            record_parity(f"{tag}/param_{k}", pv.detach().cpu().numpy(), g[o + "p_" + k], rtol=1e-3, atol=0.05 * lr)
         if kw["return_scaling"]:
             np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var, algo.ret_rms.count], g[o + "rms"], rtol=1e-5)
         assert stats.train_time > 0
@@ -263,6 +270,65 @@ def test_large_rollout_update_vs_oracle(bs):
         np.testing.assert_allclose(pv.detach().cpu().numpy(), p[k], rtol=2e-3, atol=3e-5, err_msg=k)
     np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var, algo.ret_rms.count],
                                [rms.mean, rms.var, rms.count], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name,E,T,bs,repeat", [("C2_full", 4096, 128, 16384, 1), ("C5_slice", 1024, 256, 32768, 1)])
+def test_full_size_update_vs_oracle(name, E, T, bs, repeat):
+    """BASELINE configs[1] at FULL size (4096 envs x 128 steps, minibatch 16384) and a configs[4]-shaped slice (256-step
+    rollouts, minibatch N/8) through the public ``update()``: v_s / returns / adv / logp_old at the north star's 1e-5,
+    the per-minibatch loss table row by row, and the post-update parameters, against the numpy oracle."""
+    from oracle import oracle_c
+    from tianshou_b200.data import VectorReplayBuffer
+    from tianshou_b200.synthetic import fill_vector_buffer
+    from tianshou_b200.utils import policy_within_training_step
+    kw = dict(gamma=0.99, gae_lambda=0.95, max_grad_norm=0.5, vf_coef=0.25, ent_coef=0.0, return_scaling=True,
+              eps_clip=0.2, value_clip=True, dual_clip=None, advantage_normalization=False, recompute_advantage=True)
+    algo, actor, critic = build_ppo(17, 6, DEV, **kw)
+    p = {k: v.detach().cpu().numpy().copy() for k, v in named_params(actor, critic).items()}
+    buf = VectorReplayBuffer(E * T, E, device=DEV)
+    fill_vector_buffer(buf, np.random.default_rng(5), E, T, 17, 6)
+    N = E * T
+    last = np.arange(E) * T + T - 1
+    unf = np.zeros(N, dtype=bool)
+    unf[last] = ~buf.done[last]
+    roll = dict(obs=buf.obs.copy(), obs_next=buf.obs_next.copy(), act=buf.act.copy(), rew=buf.rew.copy(),
+                terminated=buf.terminated.copy(), truncated=buf.truncated.copy(), unfinished=unf)
+    np.random.seed(11)
+    perms = np.stack([np.random.permutation(N) for _ in range(repeat)])
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(vv) for k, vv in p.items()}
+    hp = dict(eps_clip=0.2, dual_clip=None, vf_coef=0.25, ent_coef=0.0, max_grad_norm=0.5, adv_eps=1e-8, value_clip=True,
+              advantage_normalization=False, lr=3e-4, beta1=0.9, beta2=0.999, adam_eps=1e-8, weight_decay=0.0)
+    rms = onp.RunningMeanStd()
+    gae_py = onp.gae
+    onp.gae = lambda v_s, v_s_, rew, end, gamma, lam: oracle_c.gae(v_s, v_s_, rew, end, gamma, lam)   # the C loop (numba in the reference)
+    try:
+        res = onp.ppo_update(p, m, v, 0, roll, perms, bs, repeat, hp, rms, 0.99, 0.95, True)
+    finally:
+        onp.gae = gae_py
+    captured = {}
+    orig = algo._preprocess_batch
+
+    def hook(batch, buffer, indices):
+        b = orig(batch, buffer, indices)
+        captured.update({k: b[k].detach().cpu().numpy().copy() for k in ("v_s", "returns", "adv", "logp_old")})
+        return b
+
+    algo._preprocess_batch = hook
+    np.random.seed(11)
+    with policy_within_training_step(algo.policy):
+        stats = algo.update(buffer=buf, batch_size=bs, repeat=repeat)
+    assert stats.gradient_steps == repeat * (N // bs)
+    for k in ("v_s", "returns", "adv", "logp_old"):
+        ref = res["first"][k]
+        record_parity(f"{name}/{k}", captured[k], ref, rtol=1e-5, atol=1e-5 * float(np.abs(ref).max()))
+    table = algo.last_loss_table
+    for col, nm in enumerate(["loss", "actor_loss", "vf_loss", "ent_loss"]):
+        ref = res["losses"][:, col]
+        record_parity(f"{name}/per_step_{nm}", table[:, col], ref, rtol=2e-4, atol=2e-5 * max(1e-3, float(np.abs(ref).max())))
+    for k, pv in named_params(actor, critic).items():
+        record_parity(f"{name}/param_{k}", pv.detach().cpu().numpy(), p[k], rtol=1e-3, atol=0.05 * 3e-4)
+    np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var, algo.ret_rms.count], [rms.mean, rms.var, rms.count], rtol=1e-5)
 
 
 def test_policy_forward_fused_inference_matches_torch_modules():

@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from test_oracle import GAE_KATS, NSTEP_KATS
+from ts_testutil import load_golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -142,3 +143,27 @@ def test_ignore_obs_next_and_stacking():
     # last frame of every stack is the slot's own obs; obs_next's last frame is obs[next(idx)]
     assert np.array_equal(b.obs[:, -1], buf.obs[idx])
     assert np.array_equal(b.obs_next[:, -1], buf.obs[buf.next(idx)])
+
+
+def test_from_data_buffer_indices_vs_reference():
+    """``ReplayBuffer.from_data`` leaves ``_insertion_idx`` = 0 and ``last_index`` = 0 with size = N
+    (buffer_base.py:382-418): ``sample_indices(0)`` must be ``arange(N)`` -- not the rotation the kernel used to derive
+    from ``last_index + 1`` -- and keep following the insertion index through later ``add`` calls.  Golden =
+    outputs of the imported reference (``oracle/gen_golden.py fromdata``)."""
+    from tianshou_b200.data import Batch, ReplayBuffer
+    g = load_golden("fromdata_ref.npz")
+    for case in range(int(g["n_cases"])):
+        p = f"fd{case}_"
+        buf = ReplayBuffer.from_data(g[p + "obs"], g[p + "act"], g[p + "rew"], g[p + "terminated"], g[p + "truncated"],
+                                     g[p + "terminated"] | g[p + "truncated"], g[p + "obs_next"])
+        for j in range(int(g[p + "extra"])):
+            a = p + f"add{j}_"
+            buf.add(Batch(obs=g[a + "obs"], act=g[a + "act"], rew=float(g[a + "rew"]), terminated=bool(g[a + "terminated"]),
+                          truncated=bool(g[a + "truncated"]), obs_next=g[a + "obs_next"]))
+        n = int(g[p + "len"])
+        assert len(buf) == n
+        assert np.array_equal(buf.sample_indices(0), g[p + "all"]), f"case {case}"
+        q = g[p + "query"] % n
+        assert np.array_equal(buf.prev(q), g[p + "prev"]) and np.array_equal(buf.next(q), g[p + "next"])
+        assert np.array_equal(buf.unfinished_index(), g[p + "unfinished"])
+        assert np.array_equal(np.asarray(buf.done, dtype=bool), g[p + "done"])

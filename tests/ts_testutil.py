@@ -118,3 +118,27 @@ def synth_rollout(rng, E, steps, obs_dim, act_dim, p_term=1e-3, trunc_len=1000):
         done = term | trunc
         t_in_ep[done] = 0
         obs = np.where(done[:, None], rng.standard_normal((E, obs_dim)).astype(np.float32), obs_next)
+
+
+# ---- observed-error bookkeeping: every parity test records what it measured; tests/conftest.py dumps the table to
+# gpurun_out/parity_report.json at the end of the session (copied to profiles/ per round)
+PARITY: dict = {}
+
+
+def record_parity(key: str, got, ref, rtol: float, atol: float) -> dict:
+    """Assert ``|got - ref| <= atol + rtol * |ref|`` elementwise and record the observed errors under ``key``."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, f"{key}: shape {got.shape} vs {ref.shape}"
+    err = np.abs(got - ref)
+    scale = float(np.abs(ref).max()) if ref.size else 0.0
+    worst = float((err - (atol + rtol * np.abs(ref))).max()) if ref.size else 0.0
+    e = {"n": int(ref.size), "max_abs_err": float(err.max()) if ref.size else 0.0, "max_abs_ref": scale,
+         "max_err_over_max_ref": float(err.max() / scale) if scale > 0 else 0.0,
+         "rtol": rtol, "atol": atol, "margin": -worst, "ok": bool(worst <= 0.0)}
+    prev = PARITY.get(key)
+    if prev is None or e["max_err_over_max_ref"] >= prev["max_err_over_max_ref"]:
+        PARITY[key] = e
+    assert worst <= 0.0, (f"{key}: max |err| {e['max_abs_err']:.3e} (max |ref| {scale:.3e}, ratio {e['max_err_over_max_ref']:.3e}) "
+                          f"exceeds atol {atol:g} + rtol {rtol:g} * |ref| by {worst:.3e}")
+    return e

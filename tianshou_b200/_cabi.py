@@ -64,7 +64,7 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_prev_index": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P],
     "ts_stack_next_indices": [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _P],
     "ts_unfinished_index": [_P, _I64, _P, _P, _P, _P, _P, _P],
-    "ts_sample_all_indices": [_P, _I64, _P, _P, _P, _P, _I64, _P, _P],
+    "ts_sample_all_indices": [_P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ts_mark_members": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P],
     "ts_gather_rows": [_P, _I64, _P, _I64, _P, _P],
     "ts_scatter_rows": [_P, _I64, _P, _I64, _P, _P],

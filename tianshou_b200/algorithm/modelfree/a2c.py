@@ -125,6 +125,17 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         for k in ("obs", "act", "rew", "terminated", "truncated", "done"):
             if k not in meta_host.get_keys() or isinstance(meta_host[k], Batch):
                 raise UnsupportedModelError(f"fused update needs a dense '{k}' array in the buffer")
+        # the kernels stride the columns by the network descriptor: refuse layouts they would mis-read (the reference
+        # would stack frames, buffer_base.py:557-603, or fail with a shape error in the first Linear)
+        if getattr(buffer, "stack_num", 1) != 1 or getattr(buffer, "_save_only_last_obs", False):
+            raise UnsupportedModelError("fused update: frame stacking (stack_num > 1 / save_only_last_obs) is not supported "
+                                        "by the MLP actor-critic kernels")
+        obs_w = int(np.prod(meta_host.obs.shape[1:], dtype=np.int64))
+        act_w = int(np.prod(meta_host.act.shape[1:], dtype=np.int64))
+        want_act = 1 if self._desc.flags & AC_CATEGORICAL else int(self._desc.act_dim)
+        if obs_w != int(self._desc.obs_dim) or act_w != want_act:
+            raise ValueError(f"buffer rows (obs width {obs_w}, act width {act_w}) do not match the networks "
+                             f"(obs_dim {int(self._desc.obs_dim)}, action width {want_act})")
         n = len(buffer)
         full = n == buffer.maxsize and bool(np.all(buffer._ins == 0))
         need = ("obs", "act", "rew", "terminated", "truncated", "done") + (("obs_next",) if buffer._save_obs_next else ())
@@ -144,7 +155,7 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
                 up[k] = up[k].reshape(buffer.maxsize, -1)
         meta = ops.DeviceBufferMeta(
             to_device(buffer._extend_offset, dev), done_dev,
-            to_device(buffer.last_index, dev), to_device(buffer._sizes, dev))
+            to_device(buffer.last_index, dev), to_device(buffer._sizes, dev), to_device(buffer._ins, dev))
         if full:
             indices = torch.arange(n, dtype=torch.int64, device=dev)
             cols = up
@@ -234,6 +245,9 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
     def _stats_from_device(self, stats: torch.Tensor) -> A2CTrainingStats:
         """ONE D2H for all per-minibatch losses (vs 4 ``.item()`` per step, ppo.py:213-216)."""
         s = stats.cpu().numpy().astype(np.float64)
+        # per-minibatch (loss, clip/actor loss, vf loss, entropy, grad norm, rows) of the last update, in step order: what
+        # the reference appends to its four lists per optimiser step (ppo.py:213-216)
+        self.last_loss_table = s[:, :6].copy()
         return A2CTrainingStats(
             loss=SequenceSummaryStats.from_sequence(s[:, 0]),
             actor_loss=SequenceSummaryStats.from_sequence(s[:, 1]),

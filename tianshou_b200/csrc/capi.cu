@@ -19,15 +19,20 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;  // B200
+int device_ordinal() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+int num_sms() {      // of the CURRENT device (the one the caller's stream and tensors live on)
+    static int sms[kMaxDevices] = {};
+    const int dev = device_ordinal();
+    if (sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;  // B200
+        sms[dev] = n;
     }
-    return sms;
+    return sms[dev];
 }
 }  // namespace tsb
 

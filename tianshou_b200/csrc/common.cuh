@@ -53,6 +53,8 @@ inline int check_launch(const char* what) {
 
 inline cudaStream_t as_stream(ts_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+constexpr int kMaxDevices = 64;
+int device_ordinal();   // cudaGetDevice(), clamped to [0, kMaxDevices): key of per-device one-time setup caches
 int num_sms();
 
 __host__ __device__ inline int64_t imin(int64_t a, int64_t b) { return a < b ? a : b; }

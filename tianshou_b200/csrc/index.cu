@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(1024) seg_start_kernel(const int64_t* __restri
 __global__ void sample_all_kernel(const int64_t* __restrict__ offset, int64_t E,
                                   const int64_t* __restrict__ last_index,
                                   const int64_t* __restrict__ lengths,
+                                  const int64_t* __restrict__ ins_idx /* nullable */,
                                   const int64_t* __restrict__ seg_start, int64_t* __restrict__ out,
                                   int64_t capacity) {
     const int64_t total = seg_start[E];
@@ -154,8 +155,10 @@ __global__ void sample_all_kernel(const int64_t* __restrict__ offset, int64_t E,
         const int64_t size = lengths[e];
         const int64_t start = offset[e];
         const int64_t cap = offset[e + 1] - start;
-        const int64_t ins = (last_index[e] - start + 1) % cap;  // child's _insertion_idx
-        out[p] = start + (ins + j) % size;                      // [ins..size) ++ [0..ins)
+        // child's _insertion_idx (buffer_base.py:519-525).  It is NOT always last_index + 1: from_data() / dropnull()
+        // / set_batch() leave last_index untouched, so the caller passes the buffer's own counter when it has one.
+        const int64_t ins = ins_idx ? ins_idx[e] : (last_index[e] - start + 1) % cap;
+        out[p] = start + (ins % size + j) % size;               // [ins..size) ++ [0..ins)  (ins == size: arange(size))
     }
 }
 
@@ -296,8 +299,8 @@ extern "C" int ts_unfinished_index(const int64_t* offset, int64_t E, const uint8
 }
 
 extern "C" int ts_sample_all_indices(const int64_t* offset, int64_t E, const int64_t* last_index,
-                                     const int64_t* lengths, int64_t* seg_start, int64_t* out,
-                                     int64_t out_capacity, int64_t* total_out, ts_stream_t stream) {
+                                     const int64_t* lengths, const int64_t* insertion_idx, int64_t* seg_start,
+                                     int64_t* out, int64_t out_capacity, int64_t* total_out, ts_stream_t stream) {
     TS_REQUIRE(offset && last_index && lengths && seg_start && out && total_out && E > 0,
                "ts_sample_all_indices: null pointer");
     cudaStream_t st = tsb::as_stream(stream);
@@ -305,7 +308,7 @@ extern "C" int ts_sample_all_indices(const int64_t* offset, int64_t E, const int
     if (tsb::check_launch("ts_sample_all_indices/scan")) return 1;
     if (out_capacity == 0) return 0;
     const unsigned grid = (unsigned)tsb::imin((int64_t)blocks_for(out_capacity, 256), 148 * 16);
-    sample_all_kernel<<<grid, 256, 0, st>>>(offset, E, last_index, lengths, seg_start, out, out_capacity);
+    sample_all_kernel<<<grid, 256, 0, st>>>(offset, E, last_index, lengths, insertion_idx, seg_start, out, out_capacity);
     return tsb::check_launch("ts_sample_all_indices");
 }
 

@@ -872,10 +872,11 @@ int check_desc(const ts_actor_critic_desc* d, const char* fn) {
 
 template <typename K>
 int set_smem(K kernel, size_t bytes, const char* fn) {
-    static thread_local size_t configured = 0;  // per kernel instantiation
-    if (bytes > configured) {
+    static thread_local size_t configured[tsb::kMaxDevices] = {};  // per kernel instantiation and device
+    const int dev = tsb::device_ordinal();
+    if (bytes > configured[dev]) {
         TS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = bytes;
+        configured[dev] = bytes;
     }
     (void)fn;
     return 0;

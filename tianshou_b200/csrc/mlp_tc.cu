@@ -1235,11 +1235,12 @@ bool tc_supported(const ts_actor_critic_desc& d) {
 }
 
 static int configure_ppo_smem(size_t smem) {
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[kMaxDevices] = {};       // the opt-in is a per-device function attribute
+    const int dev = device_ordinal();
+    if (smem > configured[dev]) {
         TS_CUDA(cudaFuncSetAttribute(ppo_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TS_CUDA(cudaFuncSetAttribute(ppo_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        configured[dev] = smem;
     }
     return 0;
 }
@@ -1297,11 +1298,12 @@ int64_t weight_image_bytes(const ts_actor_critic_desc& d) {
 int launch_forward_tc(int mode, const float* params, const ts_actor_critic_desc& d, const float* in0, float* out0,
                       const float* in1, float* out1, int64_t n, cudaStream_t st) {
     const size_t smem = make_smem_f(d.obs_dim, 0).total;
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[mode]) {
+    static size_t configured[kMaxDevices][2] = {};
+    const int dev = device_ordinal();
+    if (smem > configured[dev][mode]) {
         if (mode == 0) TS_CUDA(cudaFuncSetAttribute(forward_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else TS_CUDA(cudaFuncSetAttribute(forward_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[mode] = smem;
+        configured[dev][mode] = smem;
     }
     const int64_t tiles = ((n + kRows - 1) / kRows) * ((mode == 0 && in1) ? 2 : 1);
     const unsigned grid = (unsigned)imin(tiles, num_sms());

@@ -225,7 +225,7 @@ class ReplayBuffer:
             if done is None or (isinstance(done, Batch)):
                 done = np.zeros(self.maxsize, dtype=bool)
             self.__dict__["_mirror"] = ops.DeviceBufferMeta.from_host(
-                self._extend_offset, done, self.last_index, self._sizes, self.device)
+                self._extend_offset, done, self.last_index, self._sizes, self.device, ins=self._ins)
             self.__dict__["_mirror_version"] = self._version
         return self._mirror
 

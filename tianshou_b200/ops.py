@@ -96,6 +96,7 @@ class DeviceBufferMeta:
     done: torch.Tensor        # uint8[B]
     last_index: torch.Tensor  # int64[E]
     lengths: torch.Tensor     # int64[E]
+    ins: torch.Tensor | None = None   # int64[E] per-sub-buffer insertion index (None: derived from last_index)
 
     @property
     def E(self) -> int:
@@ -107,13 +108,14 @@ class DeviceBufferMeta:
 
     @staticmethod
     def from_host(offset: np.ndarray, done: np.ndarray, last_index: np.ndarray, lengths: np.ndarray,
-                  device: torch.device | str | None = None) -> "DeviceBufferMeta":
+                  device: torch.device | str | None = None, ins: np.ndarray | None = None) -> "DeviceBufferMeta":
         dev = _dev(device)
         return DeviceBufferMeta(
             to_device(np.asarray(offset, dtype=np.int64), dev),
             to_device(np.asarray(done, dtype=bool), dev),
             to_device(np.asarray(last_index, dtype=np.int64), dev),
             to_device(np.asarray(lengths, dtype=np.int64), dev),
+            None if ins is None else to_device(np.asarray(ins, dtype=np.int64), dev),
         )
 
     def _args(self) -> tuple:
@@ -171,7 +173,7 @@ def sample_all_indices(meta: DeviceBufferMeta, capacity: int | None = None) -> t
     out = torch.empty(cap, dtype=torch.int64, device=meta.device)
     seg = torch.empty(meta.E + 1, dtype=torch.int64, device=meta.device)
     tot = torch.zeros(1, dtype=torch.int64, device=meta.device)
-    call("ts_sample_all_indices", ptr(meta.offset), meta.E, ptr(meta.last_index), ptr(meta.lengths),
+    call("ts_sample_all_indices", ptr(meta.offset), meta.E, ptr(meta.last_index), ptr(meta.lengths), ptr(meta.ins),
          ptr(seg), ptr(out), cap, ptr(tot), stream_ptr(meta.device))
     return out[: int(tot.item())]
 
