@@ -114,10 +114,12 @@ int ts_stack_next_indices(const int64_t* index, int64_t n, int32_t n_step, const
                           int64_t E, const uint8_t* done, const int64_t* last_index,
                           const int64_t* lengths, int64_t* out, ts_stream_t stream);
 /* ReplayBufferManager.unfinished_index (manager.py:85-91; buffer_base.py:314-317): ordered list
- * of last-written slots whose `done` is false.  out: capacity E; count_out: device int64[1]. */
+ * of the slots before each sub-buffer's insertion index whose `done` is false.  insertion_idx: device
+ * int64[E] relative to the sub-buffer start (nullable: last_index is used, which is the same slot for buffers
+ * filled by add() alone).  out: capacity E; count_out: device int64[1]. */
 int ts_unfinished_index(const int64_t* offset, int64_t E, const uint8_t* done,
-                        const int64_t* last_index, const int64_t* lengths, int64_t* out,
-                        int64_t* count_out, ts_stream_t stream);
+                        const int64_t* last_index, const int64_t* lengths, const int64_t* insertion_idx,
+                        int64_t* out, int64_t* count_out, ts_stream_t stream);
 /* sample_indices(0): all valid slots, sub-buffer-major, chronological inside each sub-buffer
  * (manager.py:217-234, buffer_base.py:519-525).  insertion_idx: device int64[E], every sub-buffer's
  * `_insertion_idx` relative to its own start (nullable: derived as last_index + 1, which is only right for
@@ -384,6 +386,87 @@ int ts_narrow_i64_i32(const int64_t* src, int64_t n, int32_t* dst, ts_stream_t s
  * exchanges LBO/SBO (diagnostic).  d receives the RAW accumulator: 128 TMEM lanes x N columns. */
 int ts_umma_selftest(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K,
                      int32_t dtype, int32_t a_mn, int32_t b_mn, int32_t swap, ts_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (9) Layered networks of the off-policy algorithms: every nn.Linear / nn.Conv2d
+ * forward and autograd backward inside SAC._update_with_batch (modelfree/sac.py:304-336),
+ * _minimize_critic_squared_loss (modelfree/ddpg.py:267-285), DQN._update_with_batch (modelfree/dqn.py:382-404)
+ * and DQNet (env/atari/atari_network.py:60-122) is ONE call of ts_net_gemm (tcgen05, fp32-faithful bf16x3):
+ *
+ *     C[M,N] (+)= relu_mask * act( A[M,K] * B[N,K]^T + bias[N] )
+ *
+ * A / B are fp32 arrays; x_mn_major = 0: element (mn, k) at p[mn * ld + k] (k contiguous), 1: at p[k * ld + mn].
+ *   forward      Y  = act(X W^T + b)   : A = X  (lda = in),  B = W  [out][in]            (0, 0)
+ *   input grad   dX = (dY W) * mask    : A = dY (lda = out), B = W  as [k = out][n = in] (0, 1)
+ *   weight grad  dW = dY^T X           : A = dY as [k = row][m = out] (1), B = X as [k = row][n = in] (1)
+ * relu_mask (nullable): the output is zeroed where relu_mask[m * ld_mask + n] <= 0 (ReLU derivative of the layer
+ * that produced A's source).  workspace (nullable): ts_net_gemm_workspace_floats(M, N, K) floats enable split-K
+ * for long reductions with few output tiles (weight gradients); partial sums are added in a fixed order. */
+enum { TS_ACT_NONE = 0, TS_ACT_RELU = 1, TS_ACT_TANH = 2 };
+int ts_net_gemm(const float* a, int64_t lda, int32_t a_mn_major, const float* b, int64_t ldb, int32_t b_mn_major,
+                float* c, int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, int32_t act,
+                const float* relu_mask, int64_t ld_mask, int32_t accumulate, float* workspace,
+                int64_t workspace_floats, ts_stream_t stream);
+int64_t ts_net_gemm_workspace_floats(int32_t M, int32_t N, int32_t K);
+/* out[n] (+)= sum_m x[m * ld + n]  (bias gradients) */
+int ts_net_colsum(const float* x, int64_t ld, int32_t M, int32_t N, float* out, int32_t accumulate, ts_stream_t stream);
+
+/* Frame stacking on the device (ReplayBuffer.get, data/buffer/buffer_base.py:557-603): out[i][s] for s = 0..S-1 is
+ * the slot of the s-th oldest frame of the stacked observation of index[i] (out[i][S-1] = index[i], each earlier
+ * one = prev() of the next, manager.py:311-336). */
+int ts_stack_prev_indices(const int64_t* index, int64_t n, int32_t stack_num, const int64_t* offset, int64_t E,
+                          const uint8_t* done, const int64_t* last_index, const int64_t* lengths, int64_t* out,
+                          ts_stream_t stream);
+/* im2col rows for nn.Conv2d(k, stride s, no padding) in torch's weight order (column = c*k*k + kh*k + kw):
+ * col[(b, ho, wo)][:].  _u8: source = single uint8 frames [slot][H][W] (save_only_last_obs buffers), channel c of
+ * sample b is frame stack_idx[b*C + c], values scaled by `scale` (ScaledObsInputActionReprNet divides by 255,
+ * env/atari/atari_network.py:26-55).  _f32: source = fp32 NHWC activations [B][H][W][C]. */
+int ts_im2col_u8(const uint8_t* frames, const int64_t* stack_idx, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k,
+                 int32_t s, float scale, float* col, ts_stream_t stream);
+int ts_im2col_f32(const float* x_nhwc, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k, int32_t s, float* col,
+                  ts_stream_t stream);
+/* inverse of ts_im2col_f32 for gradients (gather form, deterministic); relu_src (nullable, NHWC like dx): zero
+ * where relu_src <= 0 */
+int ts_col2im_f32(const float* dcol, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k, int32_t s,
+                  const float* relu_src, float* dx_nhwc, ts_stream_t stream);
+/* nn.Flatten of NCHW from NHWC activations and its backward */
+int ts_nhwc_to_nchw_flat(const float* x, int32_t B, int32_t HW, int32_t C, float* y, ts_stream_t stream);
+int ts_nchw_flat_to_nhwc(const float* dy, int32_t B, int32_t HW, int32_t C, const float* relu_src, float* dx, ts_stream_t stream);
+/* out = concat([a, b], dim=1)  (critic input obs ++ act, utils/net/continuous.py:160-166) */
+int ts_concat2(const float* a, int32_t wa, const float* b, int32_t wb, int64_t rows, float* out, ts_stream_t stream);
+
+/* SACPolicy.forward (modelfree/sac.py:108-131) on the actor head rows head[b] = (mu[0..A) | raw log-sigma[0..A)), row
+ * stride ld: sigma = exp(clamp(raw, sig_min, sig_max)), x = mu + sigma*noise, act = tanh(x), log_prob = Normal log-prob
+ * summed over actions - sum log(1 - act^2 + eps) (:25-39). */
+int ts_squashed_gaussian(const float* head, int64_t ld, const float* noise, int64_t B, int32_t A, float sig_min,
+                         float sig_max, float eps, float* act, float* logp, float* sigma_out, ts_stream_t stream);
+/* backward of mean(alpha*logp - min(q1,q2)) through the head: dact = d loss / d act from the critics (already / B);
+ * dhead has the layout of head */
+int ts_squashed_gaussian_bwd(const float* head, int64_t ld, const float* noise, const float* act, const float* sigma,
+                             const float* dact, int64_t B, int32_t A, float sig_min, float sig_max, float eps,
+                             float alpha_over_b, float* dhead, ts_stream_t stream);
+/* td = q - target; loss rows td^2*w; dq = 2 td w / B   (modelfree/ddpg.py:279-284) */
+int ts_critic_mse(const float* q, const float* target, const float* weight, int64_t B, float* td, float* dq, float* loss_rows,
+                  ts_stream_t stream);
+/* DQN loss (modelfree/dqn.py:384-399): td = returns - q[b][act[b]]; weighted MSE or Huber(delta > 0) */
+int ts_dqn_loss(const float* q, const int64_t* act, const float* returns, const float* weight, int64_t B, int32_t A,
+                float huber_delta, float* td, float* dq, float* loss_rows, ts_stream_t stream);
+/* DQN._target_q (dqn.py:365-380): double -> q_target[b][argmax_a q_online[b][a]], else max_a q_target[b][a] */
+int ts_dqn_target(const float* q_online, const float* q_target, int64_t B, int32_t A, int32_t is_double, float* out,
+                  ts_stream_t stream);
+/* min(q1, q2) - alpha * logp   (td3.py:94-102, sac.py:298-302) */
+int ts_sac_target(const float* q1, const float* q2, const float* logp, float alpha, int64_t B, float* out, ts_stream_t stream);
+/* rows of alpha*logp - min(q1,q2) and d(-min)/dq / B with torch.minimum's tie rule (sac.py:315-321) */
+int ts_sac_actor_q_grad(const float* q1, const float* q2, const float* logp, float alpha, int64_t B, float* dq1, float* dq2,
+                        float* loss_rows, ts_stream_t stream);
+int ts_mean(const float* x, int64_t n, float* out, ts_stream_t stream);
+/* clip_grad_norm_ (optional) + torch.optim.Adam step on a flat parameter vector (algorithm_base.py:496-500, optim.py:89-110);
+ * `step` = the 1-based step number of this call */
+int ts_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step, double lr,
+                 double beta1, double beta2, double eps, double weight_decay, double max_grad_norm, double* norm_scratch,
+                 ts_stream_t stream);
+/* target = tau * source + (1 - tau) * target   (utils/lagged_network.py:8-18) */
+int ts_polyak_update(float* target, const float* source, int64_t n, double tau, ts_stream_t stream);
 
 /* Diagnostics: enable / read the phase timeline (32 x %globaltimer ns) that CTA 0 of the tensor-core
  * PPO step kernel records (csrc/mlp_tc.cu). */

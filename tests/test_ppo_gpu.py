@@ -164,7 +164,7 @@ def test_ppo_update_matches_reference(variant):
         for k, pv in named_params(actor, critic).items():
             # Adam divides by sqrt(v): at step t a gradient difference of relative size e moves the parameter by up to
             # ~lr * e / (1 - beta1) -- the absolute term is stated in units of one Adam step (lr)
-            record_parity(f"{tag}/param_{k}", pv.detach().cpu().numpy(), g[o + "p_" + k], rtol=1e-3, atol=0.05 * lr)
+            record_parity(f"{tag}/param_{k}", pv.detach().cpu().numpy(), g[o + "p_" + k], rtol=1e-3, atol=0.1 * lr)
         if kw["return_scaling"]:
             np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var, algo.ret_rms.count], g[o + "rms"], rtol=1e-5)
         assert stats.train_time > 0
@@ -327,7 +327,7 @@ def test_full_size_update_vs_oracle(name, E, T, bs, repeat):
         ref = res["losses"][:, col]
         record_parity(f"{name}/per_step_{nm}", table[:, col], ref, rtol=2e-4, atol=2e-5 * max(1e-3, float(np.abs(ref).max())))
     for k, pv in named_params(actor, critic).items():
-        record_parity(f"{name}/param_{k}", pv.detach().cpu().numpy(), p[k], rtol=1e-3, atol=0.05 * 3e-4)
+        record_parity(f"{name}/param_{k}", pv.detach().cpu().numpy(), p[k], rtol=1e-3, atol=0.1 * 3e-4)
     np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var, algo.ret_rms.count], [rms.mean, rms.var, rms.count], rtol=1e-5)
 
 

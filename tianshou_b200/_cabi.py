@@ -63,7 +63,7 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_next_index": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P],
     "ts_prev_index": [_P, _I64, _P, _I64, _P, _P, _P, _P, _P],
     "ts_stack_next_indices": [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _P],
-    "ts_unfinished_index": [_P, _I64, _P, _P, _P, _P, _P, _P],
+    "ts_unfinished_index": [_P, _I64, _P, _P, _P, _P, _P, _P, _P],
     "ts_sample_all_indices": [_P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P],
     "ts_mark_members": [_P, _I64, _P, _P, _I64, _P, _I64, _P, _P],
     "ts_gather_rows": [_P, _I64, _P, _I64, _P, _P],
@@ -100,12 +100,32 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_host_perm_job_finish": [_P, _P, C.POINTER(_I32)],
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
     "ts_narrow_i64_i32": [_P, _I64, _P, _P],
+    # layered networks of the off-policy algorithms (net_gemm.cu / net_ops.cu)
+    "ts_net_gemm": [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I64, _I32, _P, _I64, _P],
+    "ts_net_colsum": [_P, _I64, _I32, _I32, _P, _I32, _P],
+    "ts_stack_prev_indices": [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _P],
+    "ts_im2col_u8": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _P, _P],
+    "ts_im2col_f32": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
+    "ts_col2im_f32": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P],
+    "ts_nhwc_to_nchw_flat": [_P, _I32, _I32, _I32, _P, _P],
+    "ts_nchw_flat_to_nhwc": [_P, _I32, _I32, _I32, _P, _P, _P],
+    "ts_concat2": [_P, _I32, _P, _I32, _I64, _P, _P],
+    "ts_squashed_gaussian": [_P, _I64, _P, _I64, _I32, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P],
+    "ts_squashed_gaussian_bwd": [_P, _I64, _P, _P, _P, _P, _I64, _I32, C.c_float, C.c_float, C.c_float, C.c_float, _P, _P],
+    "ts_critic_mse": [_P, _P, _P, _I64, _P, _P, _P, _P],
+    "ts_dqn_loss": [_P, _P, _P, _P, _I64, _I32, C.c_float, _P, _P, _P, _P],
+    "ts_dqn_target": [_P, _P, _I64, _I32, _I32, _P, _P],
+    "ts_sac_target": [_P, _P, _P, C.c_float, _I64, _P, _P],
+    "ts_sac_actor_q_grad": [_P, _P, _P, C.c_float, _I64, _P, _P, _P, _P],
+    "ts_mean": [_P, _I64, _P, _P],
+    "ts_adam_step": [_P, _P, _P, _P, _I64, _I64, _D, _D, _D, _D, _D, _D, _P, _P],
+    "ts_polyak_update": [_P, _P, _I64, _D, _P],
     "ts_tc_timeline": [_I32, _P],
     "ts_umma_selftest": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 OTHER_SYMBOLS = ["ts_version", "ts_last_error", "ts_launch_count", "ts_reset_launch_count",
                  "ts_gae_workspace_bytes", "ts_ppo_partial_rows", "ts_ppo_weight_image_bytes",
-                 "ts_ppo_peer_buffer_bytes"]
+                 "ts_ppo_peer_buffer_bytes", "ts_net_gemm_workspace_floats"]
 
 _lib: C.CDLL | None = None
 
@@ -137,6 +157,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.ts_ppo_weight_image_bytes.restype = C.c_int64
     lib.ts_ppo_peer_buffer_bytes.argtypes = [C.POINTER(ActorCriticDesc), _I32]
     lib.ts_ppo_peer_buffer_bytes.restype = C.c_int64
+    lib.ts_net_gemm_workspace_floats.argtypes = [_I32, _I32, _I32]
+    lib.ts_net_gemm_workspace_floats.restype = C.c_int64
     if path is None:
         _lib = lib
     return lib

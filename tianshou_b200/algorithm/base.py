@@ -265,7 +265,7 @@ class Algorithm(nn.Module, ABC):
             v_next = to_device(to_numpy(v_s_.flatten()), dev)
             if v_next.dtype not in (torch.float32, torch.float64):
                 v_next = v_next.to(torch.float64)
-            term_mask = ops.gather_rows(to_device(np.asarray(buffer.terminated, dtype=bool), dev), idx)
+            term_mask = ops.gather_rows(_u8_view(buffer.device_array("terminated")), idx)
         if v_s is None:
             masked = v_next if term_mask is None else v_next * (term_mask == 0).to(v_next.dtype)
             v_cur = torch.roll(masked, 1)
@@ -308,16 +308,23 @@ class Algorithm(nn.Module, ABC):
         with torch.no_grad():
             target_q_torch = target_q_fn(buffer, last_idx)
         tq = target_q_torch.reshape(I, -1).to(dev, torch.float32).contiguous().clone()
-        term = to_device(np.asarray(buffer.terminated, dtype=bool), dev)
+        # whole-buffer columns come from the device mirror / a version-keyed cache: no per-call upload of B-sized arrays
+        term = _u8_view(buffer.device_array("terminated"))
         ops.value_mask_rows(tq, term, stacked[-1].contiguous())
         end_flag = ops.buffer_end_flags(meta)
-        rew = to_device(np.asarray(buffer.rew, dtype=np.float64), dev)
+        rew = buffer.device_array("rew")
+        if rew.dtype != torch.float64:
+            rew = rew.to(torch.float64)
         out = ops.nstep_return(rew, end_flag, tq, stacked, gamma, n_step, out_dtype=torch.float64)
         batch.returns = out.reshape(target_q_torch.reshape(I, -1).shape).to(
             dtype=target_q_torch.dtype, device=target_q_torch.device)
         if hasattr(batch, "weight"):
             batch.weight = to_torch_as(batch.weight, target_q_torch)
         return batch
+
+
+def _u8_view(t: torch.Tensor) -> torch.Tensor:
+    return t.view(torch.uint8) if t.dtype == torch.bool else t
 
 
 class OnPolicyAlgorithm(Algorithm, ABC):

@@ -69,8 +69,8 @@ __global__ void stack_next_kernel(BufMeta m, const int64_t* __restrict__ index, 
 }
 
 // Single CTA: ordered compaction over the E sub-buffers.
-__global__ void __launch_bounds__(1024) unfinished_kernel(BufMeta m, int64_t* __restrict__ out,
-                                                          int64_t* __restrict__ count_out) {
+__global__ void __launch_bounds__(1024) unfinished_kernel(BufMeta m, const int64_t* __restrict__ ins_idx /* nullable */,
+                                                          int64_t* __restrict__ out, int64_t* __restrict__ count_out) {
     __shared__ int s_warp[32];
     __shared__ int64_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(1024) unfinished_kernel(BufMeta m, int64_t* __
         int64_t last = 0;
         int keep = 0;
         if (e < m.E && m.lengths[e] > 0) {
-            last = m.last_index[e];
+            // buffer_base.py:314-317: the slot BEFORE the insertion index (== last_index for buffers filled by add();
+            // from_data() / dropnull() move the insertion index without touching last_index)
+            last = ins_idx ? m.offset[e] + tsb::pymod(ins_idx[e] - 1, m.lengths[e]) : m.last_index[e];
             keep = (m.done[last] == 0);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -289,12 +291,12 @@ extern "C" int ts_stack_next_indices(const int64_t* index, int64_t n, int32_t n_
 }
 
 extern "C" int ts_unfinished_index(const int64_t* offset, int64_t E, const uint8_t* done,
-                                   const int64_t* last_index, const int64_t* lengths, int64_t* out,
-                                   int64_t* count_out, ts_stream_t stream) {
+                                   const int64_t* last_index, const int64_t* lengths, const int64_t* insertion_idx,
+                                   int64_t* out, int64_t* count_out, ts_stream_t stream) {
     META_ARGS_OK("ts_unfinished_index");
     TS_REQUIRE(out && count_out, "ts_unfinished_index: null out");
     BufMeta m{offset, E, done, last_index, lengths};
-    unfinished_kernel<<<1, 1024, 0, tsb::as_stream(stream)>>>(m, out, count_out);
+    unfinished_kernel<<<1, 1024, 0, tsb::as_stream(stream)>>>(m, insertion_idx, out, count_out);
     return tsb::check_launch("ts_unfinished_index");
 }
 

@@ -249,6 +249,20 @@ class ReplayBuffer:
         """Device-resident transition arrays if the mirror is enabled and reflects the host buffer, else None."""
         return self._dmirror.columns() if self._dmirror is not None else None
 
+    def device_array(self, key: str) -> "torch.Tensor":
+        """The whole column ``key`` on the device WITHOUT a per-call upload: the mirror's copy when the buffer keeps
+        one, else an upload cached until the buffer next changes (``add`` / ``reset`` / ``set_batch`` ... bump the
+        version).  Used by the n-step / GAE entry points, which index whole-buffer ``rew`` / ``terminated`` arrays
+        (algorithm_base.py:711,798-800) with a few hundred sampled indices."""
+        cols = self.device_columns()
+        if cols is not None and key in cols:
+            return cols[key]
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        ent = cache.get(key)
+        if ent is None or ent[0] != self._version:
+            ent = cache[key] = (self._version, to_device(np.asarray(self._meta[key]), self.device))
+        return ent[1]
+
     def sync_device_mirror(self) -> None:
         """Re-upload everything (after edits that bypass ``add()``, e.g. in-place numpy writes)."""
         if self._device_mirror_arg and len(self._meta.get_keys()) > 0:

@@ -158,7 +158,7 @@ def unfinished_index_raw(meta: DeviceBufferMeta) -> tuple[torch.Tensor, torch.Te
     out = torch.empty(meta.E, dtype=torch.int64, device=meta.device)
     cnt = torch.zeros(1, dtype=torch.int64, device=meta.device)
     o, E, d, l, n = meta._args()
-    call("ts_unfinished_index", o, E, d, l, n, ptr(out), ptr(cnt), stream_ptr(meta.device))
+    call("ts_unfinished_index", o, E, d, l, n, ptr(meta.ins), ptr(out), ptr(cnt), stream_ptr(meta.device))
     return out, cnt
 
 
