@@ -419,10 +419,11 @@ int ts_stack_prev_indices(const int64_t* index, int64_t n, int32_t stack_num, co
                           ts_stream_t stream);
 /* im2col rows for nn.Conv2d(k, stride s, no padding) in torch's weight order (column = c*k*k + kh*k + kw):
  * col[(b, ho, wo)][:].  _u8: source = single uint8 frames [slot][H][W] (save_only_last_obs buffers), channel c of
- * sample b is frame stack_idx[b*C + c], values scaled by `scale` (ScaledObsInputActionReprNet divides by 255,
- * env/atari/atari_network.py:26-55).  _f32: source = fp32 NHWC activations [B][H][W][C]. */
+ * sample b is frame stack_idx[b*C + c], values = fl32(v / denom) with the division in f64 (ScaledObsInputActionReprNet
+ * divides the uint8 array by 255.0 in numpy, env/atari/atari_network.py:26-55; denom = 1 for raw values).
+ * _f32: source = fp32 NHWC activations [B][H][W][C]. */
 int ts_im2col_u8(const uint8_t* frames, const int64_t* stack_idx, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k,
-                 int32_t s, float scale, float* col, ts_stream_t stream);
+                 int32_t s, double denom, float* col, ts_stream_t stream);
 int ts_im2col_f32(const float* x_nhwc, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k, int32_t s, float* col,
                   ts_stream_t stream);
 /* inverse of ts_im2col_f32 for gradients (gather form, deterministic); relu_src (nullable, NHWC like dx): zero

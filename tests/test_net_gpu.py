@@ -86,9 +86,9 @@ def test_conv_stack_forward_backward_vs_torch():
     stack = FusedStack(layers, group)
     frames = torch.randint(0, 256, (40, 84, 84), dtype=torch.uint8, device=DEV)
     sidx = torch.randint(0, 40, (B, 4), dtype=torch.int64, device=DEV)
-    acts = stack.forward(None, B, "t", frames=(frames, sidx, 1.0 / 255.0))
+    acts = stack.forward(None, B, "t", frames=(frames, sidx, 255.0))
     q = acts[-1]
-    x = (frames[sidx].float() / 255.0).requires_grad_(False)          # [B, 4, 84, 84]
+    x = (frames[sidx].double() / 255.0).float()          # [B, 4, 84, 84]
     q_ref = ref_net(x)
     record_parity("conv_stack/q", q.cpu().numpy(), q_ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5 * float(q_ref.abs().max()))
     coef = torch.randn(B, A, device=DEV)

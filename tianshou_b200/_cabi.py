@@ -104,7 +104,7 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_net_gemm": [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I64, _I32, _P, _I64, _P],
     "ts_net_colsum": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "ts_stack_prev_indices": [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _P],
-    "ts_im2col_u8": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _P, _P],
+    "ts_im2col_u8": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _D, _P, _P],
     "ts_im2col_f32": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "ts_col2im_f32": [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P],
     "ts_nhwc_to_nchw_flat": [_P, _I32, _I32, _I32, _P, _P],

@@ -223,7 +223,7 @@ class FusedStack:
     def forward(self, x: torch.Tensor | None, rows: int, tag: str = "a", *, frames: tuple | None = None,
                 params: torch.Tensor | None = None) -> list[torch.Tensor]:
         """Returns the activation list ``[x0, y1, ..., yL]`` (``y_i`` = post-activation output of layer i; for conv layers
-        rows * Ho * Wo NHWC rows).  ``frames`` = (uint8 frames, stack_idx int64 [rows, C], scale) feeds the first conv layer
+        rows * Ho * Wo NHWC rows).  ``frames`` = (uint8 frames, stack_idx int64 [rows, C], denom) feeds the first conv layer
         straight from single-frame storage (frame-stack gather + im2col in one kernel).  ``params``: evaluate with another
         flat parameter buffer of the same layout (the lagged / target copy)."""
         self.group.ensure_adopted()
@@ -239,8 +239,8 @@ class FusedStack:
                 R = rows * L.Ho * L.Wo
                 col = self._buf((tag, "col", i), R * L.in_dim)[: R * L.in_dim].view(R, L.in_dim)
                 if i == 0 and frames is not None:
-                    fr, sidx, scale = frames
-                    call("ts_im2col_u8", ptr(fr), ptr(sidx), rows, L.C, L.H, L.W, L.k, L.s, float(scale), ptr(col), st)
+                    fr, sidx, denom = frames
+                    call("ts_im2col_u8", ptr(fr), ptr(sidx), rows, L.C, L.H, L.W, L.k, L.s, float(denom), ptr(col), st)
                 else:
                     call("ts_im2col_f32", ptr(cur), rows, L.C, L.H, L.W, L.k, L.s, ptr(col), st)
                 y = self._buf((tag, "y", i), R * L.out_dim)[: R * L.out_dim].view(R, L.out_dim)

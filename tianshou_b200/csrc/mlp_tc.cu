@@ -124,13 +124,19 @@ __device__ __forceinline__ float tanh_mufu(float x) {
 
 // D[M x N] = A * B (operand usage K-major / MN-major per flag).  WARP-LEVEL: call from all lanes of
 // one warp; K = 16 * KSTEPS.
-template <int KSTEPS>
+template <int KSTEPS, bool FULL = true>
 __device__ __forceinline__ void gemm(uint32_t d_tmem, int M, int N, const Mat& A, int a_mn, const Mat& B, int b_mn) {
     const uint32_t a_lbo = a_mn ? A.RS : 128u, a_sbo = a_mn ? 128u : A.RS, a_step = a_mn ? 2u * A.RS : 256u;
     const uint32_t b_lbo = b_mn ? B.RS : 128u, b_sbo = b_mn ? 128u : B.RS, b_step = b_mn ? 2u * B.RS : 256u;
-    umma::gemm_bf16x3_warp<KSTEPS>(d_tmem, A.base, A.part, a_lbo, a_sbo, a_step, B.base, B.part, b_lbo, b_sbo, b_step,
-                                   umma::idesc_bf16(M, N, a_mn, b_mn));
+    umma::gemm_bf16x3_warp<KSTEPS, 3, 3, FULL>(d_tmem, A.base, A.part, a_lbo, a_sbo, a_step, B.base, B.part, b_lbo, b_sbo, b_step,
+                                               umma::idesc_bf16(M, N, a_mn, b_mn));
 }
+// weight-gradient GEMMs: three-product scheme unless TS_B200_WGRAD_FULL is defined at build time
+#ifdef TS_B200_WGRAD_FULL
+constexpr bool kWgradFull = true;
+#else
+constexpr bool kWgradFull = false;
+#endif
 // TS mode: A = the bf16x3 pieces at TMEM columns cT (written by the preceding epilogue), M = 128, K = 64
 __device__ __forceinline__ void gemm_ts(uint32_t tmem, uint32_t d_col, int N, const Mat& B, int b_mn) {
     const uint32_t b_lbo = b_mn ? B.RS : 128u, b_sbo = b_mn ? 128u : B.RS, b_step = b_mn ? 2u * B.RS : 256u;
@@ -511,7 +517,7 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
                                                const NetG& g, int obs_dim, int out_dim, float* __restrict__ grad,
                                                const float (&h1)[kCols], const float (&h2)[kCols], bool first,
                                                F&& weights_dead) {
-    pipe.issue([&] { gemm<kRows / 16>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });    // dW3^T = H2^T dOut
+    pipe.issue([&] { gemm<kRows / 16, kWgradFull>(tmem + cDW3, 64, NO, S.H2, 1, S.DO, 1); });    // dW3^T = H2^T dOut
     float dz2[kCols];
     head_input_grad_compute(sm, S, out_dim, h2, dz2);          // overlaps the MMA (reads dof / w3f / registers only)
     pipe.wait();
@@ -519,7 +525,7 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
     head_input_grad_store(sm0, S, tmem, dz2);                  // H2 := dZ2 (the MMA no longer reads H2), T := dZ2
     tstamp(17);
     pipe.run([&] {
-        gemm<kRows / 16>(tmem + cDW2, 64, H + 8, S.H2, 1, S.H1, 1);                   // [dW2 | db2] = dZ2^T [H1 | 1]
+        gemm<kRows / 16, kWgradFull>(tmem + cDW2, 64, H + 8, S.H2, 1, S.H1, 1);                   // [dW2 | db2] = dZ2^T [H1 | 1]
         gemm_ts(tmem, cDH1, H, S.W2, 1);                                              // dH1 = dZ2 W2, A = dZ2 from TMEM
     });
     tstamp(18);
@@ -527,7 +533,7 @@ __device__ __forceinline__ void trunk_backward(uint8_t* sm, uint8_t* sm0, const 
     epi_dtanh(sm0, S.H1, tmem, cDH1, h1);                                             // H1 := dZ1
     tstamp(19);
     pipe.issue([&] {
-        gemm<kRows / 16>(tmem + cDW1, 64, S.KXP + 8, S.H1, 1, S.X, 1);                // [dW1 | db1] = dZ1^T [X | 1]
+        gemm<kRows / 16, kWgradFull>(tmem + cDW1, 64, S.KXP + 8, S.H1, 1, S.X, 1);                // [dW1 | db1] = dZ1^T [X | 1]
     });
     grad_out<0>(sm0, S, tmem, g, obs_dim, out_dim, grad, first);     // dW2 / db2 / dW3 leave while the MMA runs
     pipe.wait();

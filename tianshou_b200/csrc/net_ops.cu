@@ -50,7 +50,12 @@ __global__ void stack_prev_kernel(const int64_t* __restrict__ idx, int64_t n, in
 // col[(b, ho, wo)][c * k * k + kh * k + kw] = scale * x(b, c, ho * s + kh, wo * s + kw)      (torch weight order)
 // U8 source: single uint8 frames [slot][H][W]; channel c of sample b is frame stack_idx[b * C + c].
 __global__ void im2col_u8_kernel(const uint8_t* __restrict__ frames, const int64_t* __restrict__ stack_idx, int B, int C, int H, int W,
-                                 int k, int s, int Ho, int Wo, float scale, float* __restrict__ col) {
+                                 int k, int s, int Ho, int Wo, double denom, float* __restrict__ col) {
+    // value table: fl32(v / denom) with the division in f64, exactly what `obs / 255.0` (numpy, f64) followed by the cast to
+    // float32 in DQNet.forward produces (atari_network.py:48-55,120)
+    __shared__ float lut[256];
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = (float)((double)v / denom);
+    __syncthreads();
     const int Kc = C * k * k;
     const int64_t total = (int64_t)B * Ho * Wo * Kc;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -59,7 +64,7 @@ __global__ void im2col_u8_kernel(const uint8_t* __restrict__ frames, const int64
         const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho), b = (int)(row / ((int64_t)Wo * Ho));
         const int c = kk / (k * k), kh = (kk / k) % k, kw = kk % k;
         const int64_t f = stack_idx[(int64_t)b * C + c];
-        col[t] = scale * (float)frames[(f * H + (ho * s + kh)) * W + (wo * s + kw)];
+        col[t] = lut[frames[(f * H + (ho * s + kh)) * W + (wo * s + kw)]];
     }
 }
 // fp32 NHWC source [B][H][W][C]
@@ -315,10 +320,10 @@ extern "C" int ts_stack_prev_indices(const int64_t* index, int64_t n, int32_t st
     TS_LAUNCH_1D(stack_prev_kernel, n, index, n, stack_num, offset, E, done, last_index, lengths, out);
 }
 extern "C" int ts_im2col_u8(const uint8_t* frames, const int64_t* stack_idx, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k,
-                            int32_t s, float scale, float* col, ts_stream_t stream) {
+                            int32_t s, double denom, float* col, ts_stream_t stream) {
     TS_REQUIRE(frames && stack_idx && col && k >= 1 && s >= 1 && H >= k && W >= k, "ts_im2col_u8: bad argument");
     const int Ho = (H - k) / s + 1, Wo = (W - k) / s + 1;
-    TS_LAUNCH_1D(im2col_u8_kernel, (int64_t)B * Ho * Wo * C * k * k, frames, stack_idx, B, C, H, W, k, s, Ho, Wo, scale, col);
+    TS_LAUNCH_1D(im2col_u8_kernel, (int64_t)B * Ho * Wo * C * k * k, frames, stack_idx, B, C, H, W, k, s, Ho, Wo, denom, col);
 }
 extern "C" int ts_im2col_f32(const float* x_nhwc, int32_t B, int32_t C, int32_t H, int32_t W, int32_t k, int32_t s, float* col,
                              ts_stream_t stream) {

@@ -208,7 +208,10 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) { return
 
 // Warp-level version of gemm_bf16x3 with a compile-time K-step count: call from ALL lanes of one
 // warp; one elected lane issues the 6*KSTEPS MMAs.  `pieces` = 3 (full) or 1 (operand is exact in bf16).
-template <int KSTEPS, int A_PIECES = 3, int B_PIECES = 3>
+// FULL = false: three products only -- A0 B0 + A1 B0 + A0 B1 (two pieces per operand, relative error ~2^-16 per term
+// instead of ~2^-22): used for the weight-gradient GEMMs, whose results are held to 2e-4 and which are paced by the
+// per-instruction cost of their M = 64 shared-memory-operand MMAs, not by flops.
+template <int KSTEPS, int A_PIECES = 3, int B_PIECES = 3, bool FULL = true>
 __device__ __forceinline__ void gemm_bf16x3_warp(uint32_t d_tmem, uint32_t a0, uint32_t a_part, uint32_t a_lbo, uint32_t a_sbo,
                                                  uint32_t a_step, uint32_t b0, uint32_t b_part, uint32_t b_lbo, uint32_t b_sbo,
                                                  uint32_t b_step, uint32_t idesc) {
@@ -231,9 +234,9 @@ __device__ __forceinline__ void gemm_bf16x3_warp(uint32_t d_tmem, uint32_t a0, u
             }
             bool first = (k == 0);
             // smallest terms first; pairs (i, j) with i + j <= 2
-            if (A_PIECES == 3) { mma_bf16(d_tmem, A[2], B[0], idesc, first ? 0u : 1u); first = false; }
-            if (B_PIECES == 3) { mma_bf16(d_tmem, A[0], B[2], idesc, first ? 0u : 1u); first = false; }
-            if (A_PIECES == 3 && B_PIECES == 3) { mma_bf16(d_tmem, A[1], B[1], idesc, first ? 0u : 1u); first = false; }
+            if (FULL && A_PIECES == 3) { mma_bf16(d_tmem, A[2], B[0], idesc, first ? 0u : 1u); first = false; }
+            if (FULL && B_PIECES == 3) { mma_bf16(d_tmem, A[0], B[2], idesc, first ? 0u : 1u); first = false; }
+            if (FULL && A_PIECES == 3 && B_PIECES == 3) { mma_bf16(d_tmem, A[1], B[1], idesc, first ? 0u : 1u); first = false; }
             if (A_PIECES == 3) { mma_bf16(d_tmem, A[1], B[0], idesc, first ? 0u : 1u); first = false; }
             if (B_PIECES == 3) { mma_bf16(d_tmem, A[0], B[1], idesc, first ? 0u : 1u); first = false; }
             mma_bf16(d_tmem, A[0], B[0], idesc, first ? 0u : 1u);
