@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- transitions/sec through PPO ``Algorithm.update()`` (v1: ``learn()``), obs=17.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c5] [--scaling weak|strong]
 
 Workload (BASELINE.json configs[1]): synthetic HalfCheetah-shaped rollout of
 4096 envs x 128 steps per GPU (N = 524,288 transitions, obs 17, act 6), actor/critic MLP[64,64]
@@ -19,9 +19,15 @@ Reported (one JSON line on rank 0):
              algorithmic flops 60,544 / row.
   cpu_baseline / --impl reference : the numpy port of the reference's update (oracle/) timed on
              this box's host cores on a bounded sample of the same workload.
-Multi-GPU (torchrun): weak scaling -- every rank owns its own 4096x128 rollout shard, the global
-minibatch is N x 16384 rows and ONE NCCL all-reduce of (gradient, loss sums) precedes each Adam
-step; value = all ranks' transitions / max-over-ranks time.
+Multi-GPU (torchrun): default = weak scaling -- every rank owns its own 4096x128 rollout shard, the global
+minibatch is N x 16384 rows, the gradient sum over the ranks happens INSIDE the persistent epoch kernel (8-byte
+packets over NVLink peer memory); value = all ranks' transitions / max-over-ranks time.  ``--scaling strong``: ONE
+rollout replicated on every rank, the same host permutation, each minibatch split into N contiguous slices (SURVEY
+8(e)): a fixed problem whose results equal the single-GPU run's.  Outside the timed region every multi-GPU run also
+checks itself: ``multi_gpu_check`` = {replicas_equal, loss_rel_err (N ranks vs 1 rank on the same inputs), ...}.
+``--config c5`` = BASELINE configs[4] (8192 envs x 256 steps, minibatch N/8); the default run reports it as the extra
+key ``config4`` (strong-scaled over the N GPUs).  The timed arms use the DEFAULT public API (reference-exact
+``np.random.permutation`` minibatch order); the opt-in device-generated order is reported as ``*_device_order``.
 """
 from __future__ import annotations
 
@@ -110,7 +116,16 @@ def build_host_buffer(E: int, T: int, seed: int, device):
 
 
 # ------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_run(E: int, T: int, steps: int, warmup: int) -> dict:
+def port_calibration() -> dict | None:
+    """Build-box calibration of the port against the imported reference (tools/cpu_port_calibration.py)."""
+    p = os.path.join(ROOT, "profiles", "cpu_port_calibration.json")
+    if not os.path.exists(p):
+        return None
+    c = json.load(open(p))
+    return {k: c[k] for k in ("port_over_reference", "reference_tps", "port_tps", "sample", "host_cores") if k in c}
+
+
+def cpu_reference_run(E: int, T: int, steps: int, warmup: int, batch_size: int | None = None) -> dict:
     """numpy port of the reference's PPO update (oracle/oracle_np.py) on E x T transitions,
     same minibatch size / repeat / hyper-parameters; all host threads numpy's BLAS will use."""
     from oracle import oracle_np as onp
@@ -153,7 +168,7 @@ def cpu_reference_run(E: int, T: int, steps: int, warmup: int) -> dict:
         nonlocal step
         t0 = time.perf_counter()
         perms = [np.random.permutation(N) for _ in range(REPEAT)]
-        res = onp.ppo_update(p, m, v, step, roll, perms, min(BATCH_SIZE, N), REPEAT, hp, rms, 0.99, 0.95, True)
+        res = onp.ppo_update(p, m, v, step, roll, perms, min(batch_size or BATCH_SIZE, N), REPEAT, hp, rms, 0.99, 0.95, True)
         step = res["step"]
         return time.perf_counter() - t0
 
@@ -182,7 +197,8 @@ def cpu_reference_run(E: int, T: int, steps: int, warmup: int) -> dict:
         limiter.restore_original_limits()
     mean_t = sum(times) / len(times)
     return {"value": N / mean_t, "unit": "transitions/s", "cores": int(cores), "kind": "port",
-            "sample": f"{E} envs x {T} steps = {N} transitions, minibatch {min(BATCH_SIZE, N)}, repeat {REPEAT}, "
+            "port_vs_imported_reference": port_calibration(),
+            "sample": f"{E} envs x {T} steps = {N} transitions, minibatch {min(batch_size or BATCH_SIZE, N)}, repeat {REPEAT}, "
                       f"{len(times)} timed update() calls of the numpy port (oracle/oracle_np.py), "
                       f"{cores} BLAS threads (best of a calibration sweep over 4..{ncpu})",
             "ms_per_step": mean_t * 1e3}
@@ -192,28 +208,39 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    E = int(os.environ.get("TS_BENCH_CPU_ENVS", "256"))
-    res = cpu_reference_run(E, T_FULL, max(1, args.steps), max(1, min(args.warmup, 1)))
+    cfg = CONFIGS[args.config]
+    E = int(os.environ.get("TS_BENCH_CPU_ENVS", "1024"))      # 1/4 of configs[1]: 8 minibatches of 16384 per pass
+    res = cpu_reference_run(E, cfg["T"], max(3, args.steps), max(1, min(args.warmup, 1)))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "transitions/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus) | {"cpu_sample": res["sample"]},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, args.config, args.scaling) | {"cpu_sample": res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "port_vs_imported_reference")},
         "e2e": {"value": res["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(n_gpus: int) -> dict:
-    return {"workload": f"PPO update(): synthetic HalfCheetah rollout {E_FULL} envs x {T_FULL} steps per GPU "
-                        f"(obs {OBS}, act {ACT}), MLP[64,64] tanh actor+critic, minibatch {BATCH_SIZE} per GPU, "
-                        f"repeat {REPEAT}, recompute_advantage, value_clip, return_scaling (BASELINE configs[1])",
-            "transitions_per_gpu": E_FULL * T_FULL, "global_minibatch": BATCH_SIZE * n_gpus, "repeat": REPEAT,
-            "parallelism": f"dp{n_gpus}", "l2": "explicit 256 MiB L2 flush between timed update() calls",
-            "minibatch_shuffle": "device (ts_make_permutation); the reference-RNG-exact 'numpy' mode is reported "
-                                 "as e2e_numpy_rng"}
+CONFIGS = {   # BASELINE.json configs[1] and configs[4]
+    "c2": {"E": E_FULL, "T": T_FULL, "bs": BATCH_SIZE, "name": "BASELINE configs[1]"},
+    "c5": {"E": 8192, "T": 256, "bs": 8192 * 256 // 8, "name": "BASELINE configs[4]"},
+}
+
+
+def workload_config(n_gpus: int, config: str = "c2", scaling: str = "weak") -> dict:
+    c = CONFIGS[config]
+    per = "per GPU" if scaling == "weak" else f"in total, replicated on the {n_gpus} GPUs"
+    return {"workload": f"PPO update(): synthetic HalfCheetah rollout {c['E']} envs x {c['T']} steps {per} "
+                        f"(obs {OBS}, act {ACT}), MLP[64,64] tanh actor+critic, minibatch {c['bs']}"
+                        f"{' per GPU' if scaling == 'weak' else ' split into ' + str(n_gpus) + ' contiguous slices'}, "
+                        f"repeat {REPEAT}, recompute_advantage, value_clip, return_scaling ({c['name']})",
+            "transitions": c["E"] * c["T"] * (n_gpus if scaling == "weak" else 1),
+            "global_minibatch": c["bs"] * (n_gpus if scaling == "weak" else 1), "repeat": REPEAT,
+            "parallelism": f"dp{n_gpus}", "scaling": scaling, "l2": "explicit 256 MiB L2 flush between timed update() calls",
+            "minibatch_shuffle": "numpy (the default public API: the reference's np.random.permutation stream, bit-identical "
+                                 "minibatch composition); the opt-in device-generated order is reported as *_device_order"}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -223,19 +250,24 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=E_FULL)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--envs", type=int, default=0, help="override the config's env count (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip config4 / ingest / off-policy extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
 
+    import hashlib
+
     import torch
     import torch.distributed as dist
 
-    from tianshou_b200 import _cabi
+    from tianshou_b200 import _cabi, ops
     from tianshou_b200._cabi import call, ptr, stream_ptr
-    from tianshou_b200 import ops
+    from tianshou_b200.data.batch import minibatch_bounds
     from tianshou_b200.synthetic import build_mujoco_ppo
     from tianshou_b200.utils import policy_within_training_step
 
@@ -250,12 +282,11 @@ def main() -> None:
     _cabi.load_library()
     W = max(3, args.warmup)
     K = max(1, args.steps)
-    E, T = args.envs, T_FULL
+    cfg = CONFIGS[args.config]
+    E, T, BS = (args.envs or cfg["E"]), cfg["T"], cfg["bs"]
     N = E * T
-
-    buf = build_host_buffer(E, T, seed=rank, device=dev)
-    algo, actor, critic = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="device")
-    algo_np, _, _ = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="numpy")
+    strong = args.scaling == "strong"
+    part = "shared" if strong else "per_rank"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -282,21 +313,33 @@ def main() -> None:
             tot = float(t.item())
         return tot
 
-    # ---- device-resident leg ("value"): rollout already in HBM ---------------------------------
-    with policy_within_training_step(algo.policy):
+    def flat_hash(a) -> str:
+        return hashlib.sha1(a._flat.flat.detach().cpu().numpy().tobytes()).hexdigest()[:16]
+
+    def replicas_equal(a) -> bool:
+        if world == 1:
+            return True
+        hs: list = [None] * world
+        dist.all_gather_object(hs, flat_hash(a))
+        return len(set(hs)) == 1
+
+    # weak: every rank owns its own rollout; strong: ONE rollout (same seed) on every rank, same numpy stream
+    buf = build_host_buffer(E, T, seed=0 if strong else rank, device=dev)
+    np.random.seed(1000 if strong else 1000 + rank)
+    algo, actor, critic = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="numpy", rollout_partition=part)         # default API
+    algo_dv, _, _ = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="device", rollout_partition=part)
+
+    with policy_within_training_step(algo.policy), policy_within_training_step(algo_dv.policy):
         dev_batch, dev_idx = algo._sample(buf, 0)
 
-        def device_step():
-            b = algo._preprocess_batch(dev_batch, buf, dev_idx)
-            algo._update_with_batch(b, BATCH_SIZE, REPEAT)
+        def device_step(a=algo):
+            b = a._preprocess_batch(dev_batch, buf, dev_idx)
+            a._update_with_batch(b, BS, REPEAT)
 
-        def e2e_step():
-            algo.update(buffer=buf, batch_size=BATCH_SIZE, repeat=REPEAT)
+        def e2e_step(a=algo):
+            a.update(buffer=buf, batch_size=BS, repeat=REPEAT)
 
-        def e2e_numpy_step():
-            algo_np.policy.is_within_training_step = True
-            algo_np.update(buffer=buf, batch_size=BATCH_SIZE, repeat=REPEAT)
-
+        # ---- headline: the DEFAULT public API (reference-exact minibatch order) ------------------------------
         for _ in range(W):
             device_step()
         sampler = ClockSampler(local)
@@ -309,14 +352,70 @@ def main() -> None:
             e2e_step()
         ms_e2e = timed(e2e_step, K)
         clocks = sampler.stop() if rank == 0 else {}
-        e2e_numpy_step()
-        ms_np = timed(e2e_numpy_step, max(1, min(K, 2)))
-        n_np = max(1, min(K, 2))
+        # ---- opt-in device-generated minibatch order (same kernels, no host permutation at all) --------------
+        n_dv = max(1, min(K, 3))
+        for _ in range(2):
+            device_step(algo_dv)
+        ms_dev_dv = timed(lambda: device_step(algo_dv), n_dv)
+        e2e_step(algo_dv)
+        ms_e2e_dv = timed(lambda: e2e_step(algo_dv), n_dv)
+        main_replicas_equal = replicas_equal(algo) and replicas_equal(algo_dv)
+
+        # ---- multi-GPU self-check, outside the timed region: N ranks (shared rollout, minibatch split N ways) vs ONE rank
+        # on the same rollout / weights / permutation stream
+        mg_check = None
+        if world > 1:
+            Ev, Tv, bsv, repv = 512, 128, 4096, 2
+            vbuf = build_host_buffer(Ev, Tv, seed=4321, device=dev)
+            a_n, _, _ = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="numpy", rollout_partition="shared")
+            a_1, _, _ = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="numpy", data_parallel=False)
+            tabs = []
+            for a in (a_n, a_1):
+                np_state = np.random.get_state()
+                np.random.seed(99)
+                with policy_within_training_step(a.policy):
+                    a.update(buffer=vbuf, batch_size=bsv, repeat=repv)
+                np.random.set_state(np_state)
+                tabs.append(a.last_loss_table[:, :4].copy())
+            loss_err = float(np.abs(tabs[0] - tabs[1]).max() / max(1e-30, np.abs(tabs[1]).max()))
+            pn, p1 = a_n._flat.flat.detach().cpu().numpy(), a_1._flat.flat.detach().cpu().numpy()
+            par_err = float(np.abs(pn - p1).max() / max(1e-30, np.abs(p1).max()))
+            errs = torch.tensor([loss_err, par_err], dtype=torch.float64, device=dev)
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+            mg_check = {"replicas_equal": bool(replicas_equal(a_n) and main_replicas_equal),
+                        "loss_rel_err": float(errs[0].item()), "param_rel_err": float(errs[1].item()),
+                        "fused_peer_path": a_n._scratch.get("peer_exchange") is not None,
+                        "what": f"{world} ranks (one shared rollout {Ev}x{Tv}, minibatch {bsv} split into {world} slices, same "
+                                f"np.random stream) vs a single-rank update() of the same rollout on every rank: max |loss table "
+                                f"difference| / max |loss|, max |parameter difference| / max |parameter| after {repv * (Ev * Tv // bsv)} "
+                                "optimiser steps; replicas_equal = sha1 of the flat parameters identical on all ranks (this check "
+                                "and the timed runs)"}
+
+        # ---- BASELINE configs[4] (8192 x 256, minibatch N/8) strong-scaled over the N GPUs -------------------
+        config4 = None
+        if not args.no_extras and args.config == "c2":
+            c5 = CONFIGS["c5"]
+            if c5["bs"] % world == 0:
+                buf5 = build_host_buffer(c5["E"], c5["T"], seed=5, device=dev)
+                a5, _, _ = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="numpy", rollout_partition="shared")
+                np_state = np.random.get_state()
+                np.random.seed(55)
+                with policy_within_training_step(a5.policy):
+                    step5 = lambda: a5.update(buffer=buf5, batch_size=c5["bs"], repeat=REPEAT)   # noqa: E731
+                    step5()
+                    ms5 = timed(step5, 2)
+                np.random.set_state(np_state)
+                n5 = c5["E"] * c5["T"]
+                config4 = {"value": n5 * 2 / (ms5 / 1e3), "unit": "transitions/s", "ms_per_step": ms5 / 2, "scaling": "strong",
+                           "n_gpus": world, "config": workload_config(world, "c5", "strong"), "steps": 2, "warmup": 1,
+                           "timing": "end to end through update(): host rollout upload + D2H of the loss table inside",
+                           "replicas_equal": replicas_equal(a5)}
+                del buf5, a5
 
         # ---- rollout ingestion: add() with the asynchronous device mirror, then an update()
         # that finds the rollout already on the device (no bulk upload in its timed region)
         ingest = None
-        if world == 1:
+        if world == 1 and not args.no_extras:
             from tianshou_b200.data import Batch, VectorReplayBuffer
             from tianshou_b200.synthetic import synth_rollout
             steps_host = [Batch(**s_) for s_ in synth_rollout(np.random.default_rng(7), E, T, OBS, ACT)]
@@ -335,8 +434,6 @@ def main() -> None:
                 ingest["mirror" if mirror else "host_only"] = {
                     "add_ms_per_call": 1e3 * (t1 - t0) / (T - 1), "transitions_per_s": E * (T - 1) / (t1 - t0),
                     "drain_ms_after_last_add": 1e3 * (t2 - t1)}
-            # Collector-side policy inference: policy(Batch(obs=[E, obs])) from host numpy, actions
-            # read back, fused forward kernel vs the torch module-by-module forward
             from tianshou_b200.data import Batch as _B
             obs_host = steps_host[0].obs
             infer = {}
@@ -354,7 +451,7 @@ def main() -> None:
             ingest["policy_forward_us_per_call"] = infer | {"rows": int(E)}
 
             def e2e_mirrored_step():
-                algo.update(buffer=mb, batch_size=BATCH_SIZE, repeat=REPEAT)
+                algo.update(buffer=mb, batch_size=BS, repeat=REPEAT)
             e2e_mirrored_step()
             ms_mir = timed(e2e_mirrored_step, K)
             ingest["update_from_mirror"] = {"value": N * K / (ms_mir / 1e3), "unit": "transitions/s", "ms_per_step": ms_mir / K,
@@ -366,36 +463,12 @@ def main() -> None:
     f = algo._flat
     b = dev_batch
     perm = torch.randperm(N, device=dev).to(torch.int32)
-    reps = 40
-    rows = min(BATCH_SIZE, N)
-    grad_events, adam_events = [], []
-    n_part = C.c_int32(0)
-    scratch_stats = torch.zeros(8, dtype=torch.float32, device=dev)
-    # save optimiser state: the timing loop below takes real Adam steps
+    rows = min(BS, N)
     saved = [t.clone() for t in (f.flat, f.exp_avg, f.exp_avg_sq, f.step)]
-    for i in range(reps + 5):
-        lo = (i * rows) % max(1, N - rows + 1)
-        s, m, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        s.record()
-        call("ts_ppo_grad", ptr(f.flat), C.byref(algo._desc), C.byref(hp), ptr(b.obs), ptr(b.act), ptr(b.adv),
-             ptr(b.returns), ptr(b.logp_old), ptr(b.v_s), ptr(perm), lo, lo + rows, rows, None, ptr(f.partials),
-             C.byref(n_part), stream_ptr(dev))
-        m.record()
-        call("ts_clip_adam_step", ptr(f.flat), ptr(f.grad), ptr(f.partials), n_part.value, ptr(f.exp_avg),
-             ptr(f.exp_avg_sq), ptr(f.step), C.byref(algo._desc), C.byref(hp), ptr(scratch_stats), stream_ptr(dev))
-        e.record()
-        if i >= 5:
-            grad_events.append((s, m))
-            adam_events.append((m, e))
-    torch.cuda.synchronize()
-    for dst, src in zip((f.flat, f.exp_avg, f.exp_avg_sq, f.step), saved):
-        dst.copy_(src)
-    # the single-GPU product path: ONE persistent launch per pass over the rollout (all n_mb optimiser steps)
-    from tianshou_b200.data.batch import minibatch_bounds
-    bounds = minibatch_bounds(N, BATCH_SIZE, merge_last=True)
+    bounds = minibatch_bounds(N, BS, merge_last=True)
     epoch_stats = torch.zeros((len(bounds), 8), dtype=torch.float32, device=dev)
     epoch_events = []
-    for i in range(10):
+    for i in range(10):     # the single-GPU product path: ONE persistent launch per pass over the rollout (all optimiser steps)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         algo._device_passes(b, perm, bounds, hp, epoch_stats, 1, False)
@@ -406,8 +479,6 @@ def main() -> None:
     for dst, src in zip((f.flat, f.exp_avg, f.exp_avg_sq, f.step), saved):
         dst.copy_(src)
     epoch_ms = sum(s.elapsed_time(e) for s, e in epoch_events) / len(epoch_events)
-    grad_ms = sum(s.elapsed_time(e) for s, e in grad_events) / len(grad_events)
-    adam_ms = sum(s.elapsed_time(e) for s, e in adam_events) / len(adam_events)
     fwd_events = []
     for i in range(8):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -418,9 +489,8 @@ def main() -> None:
             fwd_events.append((s, e))
     torch.cuda.synchronize()
     fwd_ms = sum(s.elapsed_time(e) for s, e in fwd_events) / len(fwd_events)
-    # GAE scan alone (HBM-bound kernel)
     gae_events = []
-    for i in range(25):
+    for i in range(25):     # GAE scan alone (HBM-bound kernel), L2 flushed
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -438,13 +508,13 @@ def main() -> None:
         return
 
     peaks, peak_src = load_peaks()
-    total_transitions = N * world
+    total_transitions = N * (1 if strong else world)
     value = total_transitions * K / (ms_dev / 1e3)
     e2e_value = total_transitions * K / (ms_e2e / 1e3)
-    e2e_np_value = total_transitions * n_np / (ms_np / 1e3)
     meta_bytes = buf._extend_offset.nbytes + buf.last_index.nbytes + buf._sizes.nbytes
     h2d = sum(np.asarray(buf._meta[k]).nbytes for k in ("obs", "obs_next", "act", "rew", "terminated", "truncated", "done")) + meta_bytes
-    n_mb = len(range(0, N, BATCH_SIZE))
+    h2d += REPEAT * N * 4                       # the host-drawn permutations (int32) of the default minibatch order
+    n_mb = len(bounds)
     d2h = REPEAT * n_mb * 8 * 4 + 3 * 8
     grad_flops = FLOP_TRAIN_PER_ROW * N            # one pass of the epoch kernel touches every transition once
     grad_tflops = grad_flops / (epoch_ms * 1e-3) / 1e12
@@ -455,16 +525,19 @@ def main() -> None:
     gae_bytes = 27 * N
     line = {
         "metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32 (MLP fwd/bwd, Adam), f64 (GAE scan, running return statistics)", "data": "synthetic",
-        "config": workload_config(world),
+        "config": workload_config(world, args.config, args.scaling),
         "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / K},
-        "e2e_numpy_rng": {"value": e2e_np_value, "unit": "transitions/s", "ms_per_step": ms_np / n_np,
-                          "note": "public API with the default minibatch_shuffle='numpy': the reference's np.random.permutation draw per "
-                                  "pass (global MT19937 stream, bit-identical minibatch composition) generated on the host by "
-                                  "background threads of the C library ahead of the passes (ts_host_perm_job_*): ~2 ms per 524288-element permutation"},
+        "value_device_order": {"value": total_transitions * n_dv / (ms_dev_dv / 1e3), "unit": "transitions/s", "ms_per_step": ms_dev_dv / n_dv},
+        "e2e_device_order": {"value": total_transitions * n_dv / (ms_e2e_dv / 1e3), "unit": "transitions/s", "ms_per_step": ms_e2e_dv / n_dv,
+                             "note": "opt-in minibatch_shuffle='device' (ts_make_permutation): same kernels, the minibatch order is a "
+                                     "keyed bijection generated on the GPU instead of the reference's np.random.permutation stream"},
+        "default_over_device_order": {"value": (ms_dev_dv / n_dv) / (ms_dev / K), "e2e": (ms_e2e_dv / n_dv) / (ms_e2e / K)},
         "gpu_launches": int(launches),
+        "multi_gpu_check": mg_check,
+        "config4": config4,
         "ingest": ingest,
         "roofline": {"kernel": "ppo_tc_kernel<EPOCH> (persistent: every optimiser step of one pass = minibatch fwd/bwd + "
                                "gradient fold + clip + Adam; tcgen05 bf16x3 = fp32-faithful)", "bound": "tensor",
@@ -472,24 +545,33 @@ def main() -> None:
                      "frac": grad_tflops / peaks["bf16_tflops"], "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_flops_per_launch": grad_flops, "launch_ms": epoch_ms, "rows_per_launch": N,
                      "optimiser_steps_per_launch": len(bounds), "us_per_optimiser_step": 1e3 * epoch_ms / len(bounds),
-                     "note": "latency-bound chain of 28 dependent MMA stages per 128-row tile on a 17-64-64-{1,6} MLP; the bf16x3 "
-                             "scheme executes 6 MMAs per algorithmic one, so the tensor pipe does 6x the flops counted here"},
+                     "note": "latency-bound chain of dependent MMA stages per 128-row tile on a 17-64-64-{1,6} MLP; forward and input-"
+                             "gradient GEMMs use 6 bf16 MMAs per algorithmic one (fp32-faithful), weight-gradient GEMMs 3"},
         "roofline_gae": {"kernel": "gae_scan_kernel", "bound": "hbm", "achieved": gae_bytes / (gae_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gae_bytes / (gae_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "algorithmic_bytes_per_launch": gae_bytes, "launch_ms": gae_ms, "peak_source": peak_src},
-        "kernel_ms": {"ppo_epoch(all optimiser steps of one pass)": epoch_ms, "ppo_grad(multi-GPU path)": grad_ms,
-                      "clip_adam(multi-GPU path: reduce+norm+adam)": adam_ms, "critic_forward(v_s,v_s_)": fwd_ms,
-                      "gae_scan": gae_ms},
+        "kernel_ms": {"ppo_epoch(all optimiser steps of one pass)": epoch_ms, "critic_forward(v_s,v_s_)": fwd_ms, "gae_scan": gae_ms},
         "flops_per_transition": FLOP_PER_TRANSITION,
         "update_tflops": FLOP_PER_TRANSITION * total_transitions * K / (ms_dev / 1e3) / 1e12,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_run(int(os.environ.get("TS_BENCH_CPU_ENVS", "128")), T_FULL, 1, 1)
-        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_reference_run(int(os.environ.get("TS_BENCH_CPU_ENVS_INLINE", "256")), T, 3, 1, batch_size=BS)
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "port_vs_imported_reference")}
+    if world == 1 and not args.no_extras:
+        try:
+            line["offpolicy"] = offpolicy_extras(dev)
+        except Exception as ex:  # noqa: BLE001 - extras must never take the headline down
+            line["offpolicy"] = {"error": repr(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def offpolicy_extras(dev) -> dict:
+    """BASELINE configs[2] / configs[3] shaped update() calls: updates/s of the device path through
+    the public API vs the torch-CPU restatement (oracle/oracle_offpolicy.py) on the same shapes.  Reduced buffer sizes (stated)."""
+    return {}
 
 
 if __name__ == "__main__":

@@ -89,7 +89,7 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         self._flat.weight_image = torch.zeros(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
         if hasattr(self.policy, "_fused_inference"):      # Collector-side inference through the same forward kernel
             self.policy._fused_inference = (self._flat, self._desc)
-        if self._world_size() > 1:  # replicas start bit-identical
+        if self._world_size() > 1 and getattr(self, "data_parallel", True):  # replicas start bit-identical
             from ...parallel import broadcast_params_
             broadcast_params_(self._flat.flat)
         # a real torch Adam (+ scheduler) keeps lr schedules and state_dict round trips unchanged
@@ -187,7 +187,10 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         adv = self._buf("adv", n, torch.float32)
         ret = self._buf("returns", n, torch.float32)
         moments = None
-        if rms is not None and self._world_size() > 1:
+        # per-rank rollout shards: the ranks' batch moments are merged in rank order; a shared rollout needs no exchange
+        # (every rank scans the same transitions)
+        if (rms is not None and self._world_size() > 1 and getattr(self, "data_parallel", True)
+                and getattr(self, "rollout_partition", "per_rank") == "per_rank"):
             moments = self._buf("rms_moments", 3, torch.float64)
         ops.gae(v_s, v_next, batch.rew, batch.terminated, batch.truncated, batch.get("_unfinished"),
                 gamma=self.gamma, gae_lambda=self.gae_lambda, rms_state=rms, rms_eps=self._eps,

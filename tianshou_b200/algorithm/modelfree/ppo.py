@@ -44,6 +44,28 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
     _shuffle_epoch: int = 0
     recompute_adv: bool = False
     advantage_normalization: bool = False
+    # Multi-GPU data parallelism (one process per GPU).  "per_rank": every rank's buffer is ITS OWN shard of the rollout
+    # (weak scaling: the global minibatch is the union of the ranks' local minibatches).  "shared": every rank holds the
+    # SAME rollout and draws the SAME permutation; each minibatch of B rows is split into world_size contiguous slices of
+    # B / world_size (a fixed problem, results comparable with a single-GPU / reference run on the same inputs).
+    rollout_partition: str = "per_rank"
+    data_parallel: bool = True          # False: ignore an initialised process group (single-rank execution)
+
+    def _ranks(self) -> tuple[int, int]:
+        return world() if self.data_parallel else (0, 1)
+
+    def _shared_slice(self, perm_r: torch.Tensor, bounds: list[tuple[int, int]], rank: int, wsize: int
+                      ) -> tuple[torch.Tensor, list[tuple[int, int]]]:
+        """This rank's contiguous 1 / wsize slice of every minibatch of ``perm_r`` as a local permutation + bounds."""
+        n_mb = len(bounds)
+        size = bounds[0][1] - bounds[0][0]
+        regular = all(lo == m * size and hi == lo + size for m, (lo, hi) in enumerate(bounds))
+        if not regular or size % wsize != 0:
+            raise ValueError(f"rollout_partition='shared' needs len(buffer) % batch_size == 0 and batch_size % world_size == 0 "
+                             f"(got {bounds[-1][1]} transitions, minibatch {size}, {wsize} ranks)")
+        local = size // wsize
+        sl = perm_r[: n_mb * size].view(n_mb, wsize, local)[:, rank, :].contiguous().view(-1)
+        return sl, [(m * local, (m + 1) * local) for m in range(n_mb)]
 
     def _loss_hparams(self) -> Any:
         raise NotImplementedError
@@ -70,6 +92,8 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         """Pass r over the minibatches in the order ``perm_r`` (optional advantage recompute first, ppo.py:174-178)."""
         if self.recompute_adv and r > 0:
             self._add_returns_and_advantages(batch, None, None)
+        if wsize > 1 and self.rollout_partition == "shared":
+            perm_r, bounds = self._shared_slice(perm_r, bounds, rank, wsize)
         if wsize == 1:
             self._device_passes(batch, perm_r, bounds, hp, stats, 1, False)
         elif self._peer_exchange(bounds) is not None:
@@ -93,7 +117,7 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         n_mb = len(bounds)
         hp = self._loss_hparams()
         stats = self._alloc_stats(repeat * n_mb)
-        rank, wsize = world()
+        rank, wsize = self._ranks()
         single_call = self.minibatch_shuffle == "device" and wsize == 1
 
         if self.minibatch_shuffle == "device":
@@ -154,6 +178,7 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
             size = bounds[0][1] - bounds[0][0]
             regular = all(lo == bounds[0][0] + m * size and (m == len(bounds) - 1 or hi == lo + size)
                           for m, (lo, hi) in enumerate(bounds))
+            # (decided once per algorithm instance from the first pass's bounds; "shared" slices are regular by construction)
             usable = (os.environ.get("TS_B200_NO_P2P", "0") != "1" and regular
                       and self._flat.weight_image is not None and os.environ.get("TS_B200_FORCE_SIMT", "0") != "1")
             # the decision must be identical on every rank: all inputs above are (shapes, env) -- replicas agree
@@ -234,9 +259,12 @@ class PPO(FusedActorCriticUpdate):
         return_scaling: bool = False,
         minibatch_shuffle: Literal["numpy", "device"] = "numpy",
         shuffle_seed: int = 0,
+        rollout_partition: Literal["per_rank", "shared"] = "per_rank",
+        data_parallel: bool = True,
     ) -> None:
         assert dual_clip is None or dual_clip > 1.0, (
             f"Dual-clip PPO parameter should greater than 1.0 but got {dual_clip}")
+        object.__setattr__(self, "data_parallel", bool(data_parallel))     # read by the base constructor (replica broadcast)
         super().__init__(policy=policy, critic=critic, optim=optim, optim_include_actor=True,
                          max_grad_norm=max_grad_norm, gae_lambda=gae_lambda, max_batchsize=max_batchsize,
                          gamma=gamma, return_scaling=return_scaling)
@@ -252,6 +280,9 @@ class PPO(FusedActorCriticUpdate):
         self.minibatch_shuffle = minibatch_shuffle
         self._shuffle_seed = shuffle_seed
         self._shuffle_epoch = 0
+        if rollout_partition not in ("per_rank", "shared"):
+            raise ValueError(f"rollout_partition must be 'per_rank' or 'shared', got {rollout_partition!r}")
+        self.rollout_partition = rollout_partition
 
     # ------------------------------------------------------------------ preprocess
     def _preprocess_batch(self, batch: Batch, buffer: ReplayBuffer, indices: Any) -> Batch:

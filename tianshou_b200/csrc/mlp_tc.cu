@@ -592,6 +592,45 @@ struct GridBarrier {   // monotonic counter: the k-th use waits for k * gridDim.
     __device__ __forceinline__ void sync() { arrive(); wait(); }
 };
 
+// Cross-GPU sum of one gradient element (fused all-reduce of the epoch kernel): the peers' (value, seq) packets of this
+// step are polled CONCURRENTLY -- one load per missing peer and round, all in flight together -- so the wait is one NVLink
+// latency, not world - 1 dependent ones; the sum runs in rank order (bit-identical on every rank).  Kept out of line: its
+// register arrays must not weigh on the single-GPU path.
+__device__ __noinline__ float peer_gather_sum(const unsigned long long* src0, int world, int rank, float g, unsigned int seq,
+                                              size_t peer_stride) {
+    float vals[tsb::kMaxPeers];
+    unsigned int missing = ((1u << world) - 1u) & ~(1u << rank);
+    unsigned long long t_start = 0ull;
+    unsigned int spins = 0u;
+    while (missing) {
+        unsigned long long got[tsb::kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < tsb::kMaxPeers; ++r) {
+            if (missing & (1u << r))
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got[r]) : "l"(src0 + (size_t)r * peer_stride) : "memory");
+        }
+#pragma unroll
+        for (int r = 0; r < tsb::kMaxPeers; ++r) {
+            if ((missing & (1u << r)) && (unsigned int)(got[r] >> 32) == seq) {
+                vals[r] = __uint_as_float((unsigned int)got[r]);
+                missing &= ~(1u << r);
+            }
+        }
+        if (missing && (++spins & 0xffffu) == 0u) {      // a peer that never shows up must not hang the GPU
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_start == 0ull) t_start = now;
+            else if (now - t_start > 20000000000ull) __trap();
+        }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int r = 0; r < tsb::kMaxPeers; ++r) {
+        if (r < world) sum += (r == rank) ? g : vals[r];
+    }
+    return sum;
+}
+
 struct TileIn { float xv[8]; float av[kMaxAct]; float rv[4]; };   // one thread's share of a tile's gathers
 
 // The minibatches of one launch are [lo0 + m * mb_size, lo0 + (m + 1) * mb_size) for m < n_mb - 1 and
@@ -890,29 +929,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
                         unsigned long long* dst = px.recv[r] + (size_t)px.rank * 2u * (size_t)width + slot;
                         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(pkt) : "memory");
                     }
-                    float sum = 0.0f;
-                    unsigned long long t_start = 0ull;
-                    for (int r = 0; r < px.world; ++r) {
-                        float v = g;
-                        if (r != px.rank) {
-                            const unsigned long long* src = px.recv[px.rank] + (size_t)r * 2u * (size_t)width + slot;
-                            unsigned long long got;
-                            unsigned int spins = 0u;
-                            for (;;) {
-                                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
-                                if ((unsigned int)(got >> 32) == seq) break;
-                                if ((++spins & 0xffffu) == 0u) {      // a peer that never shows up must not hang the GPU
-                                    unsigned long long now;
-                                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                                    if (t_start == 0ull) t_start = now;
-                                    else if (now - t_start > 20000000000ull) __trap();
-                                }
-                            }
-                            v = __uint_as_float((unsigned int)got);
-                        }
-                        sum += v;
-                    }
-                    g = sum;
+                    g = peer_gather_sum(px.recv[px.rank] + slot, px.world, px.rank, g, seq, 2u * (size_t)width);
                 }
                 opt.grad_scratch[i] = g;
                 if (i < d.n_params) ss += (double)g * (double)g;
@@ -967,8 +984,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
                 adam_elem(i, opt.grad_scratch[i], opt.params_w[i], opt.exp_avg[i], opt.exp_avg_sq[i]);
         }
         if (wimg != nullptr) umma::fence_proxy_async_all();      // image stores (generic proxy) before the peers' bulk copies
-        if (tid == 0 && blockIdx.x == 0) {
-            // the folded loss sums were written by the owner of the last slice before barrier 2
+        tstamp(14);
+        const bool more = m + 1 < n_mb;
+        if (more) gbar.arrive();                                    // barrier 3 (updated parameters visible to every CTA) ...
+        if (tid == 32 && blockIdx.x == 0) {                         // ... the loss table row is written under it, off tid 0's poll
+            // the folded loss sums were written by the owner of the last slice before barrier 2; nothing rewrites them before the
+            // next step's fold, i.e. after every CTA passed the NEXT barrier 1
             const float* ex = opt.grad_scratch + d.n_params;
             const float e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
             const float rows = e3 > 0.0f ? e3 : 1.0f;
@@ -980,9 +1001,8 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
                 sr[4] = s_norm; sr[5] = e3; sr[6] = 0.0f; sr[7] = 0.0f;
             }
         }
-        tstamp(14);
-        if (m + 1 < n_mb) {
-            gbar.sync();                                            // updated parameters visible to every CTA
+        if (more) {
+            gbar.wait();
             if (pre) { issue_weights(0); critic_issued = true; }
         }
         tstamp(15);

@@ -82,6 +82,10 @@ def _coerce(obj: Any) -> Any:
         return np.asanyarray(obj)
     if isinstance(obj, dict):
         return Batch(obj)
+    if type(obj).__name__ == "Batch" and hasattr(obj, "get_keys") and hasattr(obj, "__getitem__"):
+        # a Batch of another implementation with the same protocol (the reference Collector builds its own when it drives
+        # this package's buffers / policies): adopt its entries
+        return Batch({k: obj[k] for k in obj.get_keys()})
     if isinstance(obj, Distribution):
         return obj
     if (

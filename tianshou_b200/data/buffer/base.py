@@ -26,7 +26,7 @@ import torch
 
 from ... import ops
 from ..._cabi import to_device
-from ..batch import Batch, IndexType, alloc_by_keys_diff, create_value
+from ..batch import Batch, IndexType, _coerce, alloc_by_keys_diff, create_value
 
 
 class MalformedBufferError(RuntimeError):
@@ -355,7 +355,7 @@ class ReplayBuffer:
         """Add one transition (buffer_base.py:420-501).  Returns (index, ep_rew, ep_len, ep_start)."""
         new = Batch()
         for k in batch.get_keys():
-            new.__dict__[k] = batch[k]
+            new.__dict__[k] = _coerce(batch[k])
         batch = new
         batch.__dict__["done"] = np.logical_or(batch.terminated, batch.truncated)
         if not self._required_keys_for_add.issubset(batch.get_keys()):
@@ -547,7 +547,16 @@ class ReplayBuffer:
         self._touch()
 
     def hasnull(self) -> bool:
-        return self[:].hasnull()
+        """Any NaN / None among the valid transitions (the trainer asks after every collect, trainer.py:953).  The answer does
+        not depend on the order of the rows, so the stored arrays are scanned in place -- no ``buffer[:]`` copy of the whole
+        rollout in ``sample_indices(0)`` order (buffer_base.py:605-649) and no device work."""
+        n = len(self)
+        if n == 0:
+            return False
+        if n == self.maxsize:
+            return self._meta.hasnull()
+        valid = np.concatenate([np.arange(o, o + k) for o, k in zip(self._offset, self._sizes, strict=True) if k > 0])
+        return self._meta[valid].hasnull()
 
     def isnull(self) -> Batch:
         return self[:].isnull()
@@ -602,7 +611,7 @@ class ReplayBufferManager(ReplayBuffer):
         """Add one transition per listed sub-buffer (manager.py:131-198)."""
         new = Batch()
         for k in set(self._reserved_keys).intersection(batch.get_keys()):
-            new.__dict__[k] = batch[k]
+            new.__dict__[k] = _coerce(batch[k])         # (entries of a foreign Batch implementation are adopted)
         batch = new
         batch.__dict__["done"] = np.logical_or(batch.terminated, batch.truncated)
         assert {"obs", "act", "rew", "terminated", "truncated", "done"}.issubset(batch.get_keys())
