@@ -380,13 +380,6 @@ int ts_make_permutation(uint64_t seed, int32_t first_epoch, int32_t n_epochs, in
 /* int64 -> int32 narrowing of a host-drawn permutation already uploaded to the device. */
 int ts_narrow_i64_i32(const int64_t* src, int64_t n, int32_t* dst, ts_stream_t stream);
 
-/* Hardware self-test of the tcgen05 / TMEM building blocks (csrc/umma.cuh), one CTA:
- * D[M,N] = a[M,K] * b[N,K]^T with dtype 0 = 3xTF32 (kind::tf32) or 1 = 3-way bf16 split (kind::f16),
- * M in {64,128}; a_mn / b_mn place the operand MN-major instead of K-major in shared memory; swap
- * exchanges LBO/SBO (diagnostic).  d receives the RAW accumulator: 128 TMEM lanes x N columns. */
-int ts_umma_selftest(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K,
-                     int32_t dtype, int32_t a_mn, int32_t b_mn, int32_t swap, ts_stream_t stream);
-
 /* ------------------------------------------------------------------------------------------
  * (9) Layered networks of the off-policy algorithms: every nn.Linear / nn.Conv2d
  * forward and autograd backward inside SAC._update_with_batch (modelfree/sac.py:304-336),
@@ -469,9 +462,20 @@ int ts_adam_step(float* params, const float* grad, float* exp_avg, float* exp_av
 /* target = tau * source + (1 - tau) * target   (utils/lagged_network.py:8-18) */
 int ts_polyak_update(float* target, const float* source, int64_t n, double tau, ts_stream_t stream);
 
+#ifdef TS_B200_DIAGNOSTICS
+/* Diagnostics build only (libts_b200_diag.so, `python -m tianshou_b200.csrc.build --diag`): not part of the product library. */
+/* Hardware self-test of the tcgen05 / TMEM building blocks (csrc/umma.cuh), one CTA:
+ * D[M,N] = a[M,K] * b[N,K]^T with dtype 0 = 3xTF32 (kind::tf32) or 1 = 3-way bf16 split (kind::f16),
+ * M in {64,128}; a_mn / b_mn place the operand MN-major instead of K-major in shared memory; swap
+ * exchanges LBO/SBO (diagnostic).  d receives the RAW accumulator: 128 TMEM lanes x N columns. */
+int ts_umma_selftest(const float* a, const float* b, float* d, int32_t M, int32_t N, int32_t K,
+                     int32_t dtype, int32_t a_mn, int32_t b_mn, int32_t swap, ts_stream_t stream);
+
 /* Diagnostics: enable / read the phase timeline (32 x %globaltimer ns) that CTA 0 of the tensor-core
  * PPO step kernel records (csrc/mlp_tc.cu). */
 int ts_tc_timeline(int32_t enable, uint64_t* out32 /* host, nullable */);
+#endif /* TS_B200_DIAGNOSTICS */
+
 
 #ifdef __cplusplus
 }

@@ -137,9 +137,13 @@ def test_device_path_fails_loudly_without_gpu():
 
 
 # ------------------------------------------------------------------------------------ C ABI
-def header_functions():
+def header_functions(diagnostics: bool = False):
     text = open(os.path.join(ROOT, "include", "ts_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    diag = re.findall(r"#ifdef TS_B200_DIAGNOSTICS(.*?)#endif", text, flags=re.S)
+    text = re.sub(r"#ifdef TS_B200_DIAGNOSTICS.*?#endif", "", text, flags=re.S)
+    if diagnostics:
+        return sorted(set(re.findall(r"\b(ts_[a-z0-9_]+)\s*\(", "".join(diag))))
     return sorted(set(re.findall(r"\b(ts_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -152,6 +156,11 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/ts_b200.h but not exported"
     bound = set(_cabi.SIGNATURES) | set(_cabi.OTHER_SYMBOLS)
     assert set(names) == bound, set(names) ^ bound
+    # diagnostics (phase timeline, tcgen05 self-test) live in a separate build and are NOT in the product library
+    diag = header_functions(diagnostics=True)
+    assert set(diag) == set(_cabi.DIAG_SIGNATURES) and len(diag) == 2
+    for n in diag:
+        assert not hasattr(lib, n), f"diagnostic entry {n} exported by the product library"
     lib2 = _cabi.load_library()
     assert lib2.ts_version() == 1
     assert lib2.ts_gae_workspace_bytes(2048 * 3 + 1) > 0

@@ -120,9 +120,29 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_mean": [_P, _I64, _P, _P],
     "ts_adam_step": [_P, _P, _P, _P, _I64, _I64, _D, _D, _D, _D, _D, _D, _P, _P],
     "ts_polyak_update": [_P, _P, _I64, _D, _P],
+}
+# diagnostics build only (libts_b200_diag.so, tools/): not part of the product library
+DIAG_SIGNATURES: dict[str, list[Any]] = {
     "ts_tc_timeline": [_I32, _P],
     "ts_umma_selftest": [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
+DIAG_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libts_b200_diag.so")
+
+
+def use_diagnostics_library() -> C.CDLL:
+    """Make the process-wide library the DIAGNOSTICS build (phase timeline, tcgen05 self-test); tools/ only."""
+    global _lib
+    if not os.path.exists(DIAG_LIB_PATH):
+        raise ExtensionMissingError(f"{DIAG_LIB_PATH} not found: build it with `python -m tianshou_b200.csrc.build --diag`")
+    _lib = None
+    lib = load_library(DIAG_LIB_PATH)
+    for name, argtypes in DIAG_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
 OTHER_SYMBOLS = ["ts_version", "ts_last_error", "ts_launch_count", "ts_reset_launch_count",
                  "ts_gae_workspace_bytes", "ts_ppo_partial_rows", "ts_ppo_weight_image_bytes",
                  "ts_ppo_peer_buffer_bytes", "ts_net_gemm_workspace_floats"]

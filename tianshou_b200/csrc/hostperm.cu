@@ -4,10 +4,10 @@
 // (batch.py:1209); nothing else consumes that stream inside Algorithm.update(), so the `repeat` draws of one
 // update can be produced ahead of the passes that use them.  The draw itself is sequential in two ways: the
 // MT19937 stream (data-dependent length because random_interval rejects) and the Fisher-Yates swaps.  A job
-// splits them: ONE producer thread walks the generator and records the accepted index j for every i
-// (~1.5 ms per 524 288-element permutation, no memory traffic besides the record), and worker threads apply the
+// splits them three ways: a GENERATOR thread runs MT19937 ahead (the word stream does not depend on how many words a
+// permutation consumes: mt_gen + vectorised tempering into a ring of blocks), ONE walker thread does the data-dependent
+// part only (mask, compare, advance: records the accepted index j for every i), and worker threads apply the
 // swaps of different passes concurrently (~2.5 ms each) straight into the caller's (pinned) int32 rows.
-// Pass r becomes available ~4 + 1.5 r ms after the start, which keeps pace with the GPU's ~1.5 ms per pass.
 // Bit-identical to np.random.permutation, including the final generator state (ts_host_perm_job_finish).
 #include <atomic>
 #include <condition_variable>
@@ -31,6 +31,19 @@ inline void mt_gen(uint32_t* key) {
     key[kMtN - 1] = key[kMtM - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
 }
 
+// One generator block: the MT19937 state after its mt_gen (numpy's `key`) and the tempered outputs of its 624 words.
+struct MtBlock {
+    uint32_t key[kMtN];
+    uint32_t temp[kMtN];
+};
+__attribute__((target_clones("avx2", "default"))) void mt_temper(const uint32_t* key, uint32_t* out) {
+    for (int d = 0; d < kMtN; ++d) {        // vectorisable: no loop-carried dependence
+        uint32_t y = key[d];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        out[d] = y;
+    }
+}
+
 struct PermJob {
     uint32_t key[kMtN];
     int pos = 0;
@@ -41,13 +54,45 @@ struct PermJob {
     std::vector<int> state;                      // 0 = pending, 1 = j-sequence ready, 2 = permutation ready
     std::mutex mu;
     std::condition_variable cv;
-    std::thread producer;
+    std::thread generator, producer;
     std::vector<std::thread> workers;
     std::atomic<int> next_apply{0};
     int applied = 0;                             // passes completely applied (guarded by mu)
-    static constexpr int kAhead = 6;             // the producer stays at most this many passes ahead of the workers
+    static constexpr int kAhead = 6;             // the walker stays at most this many passes ahead of the workers
+    // generator -> walker ring.  The MT19937 word stream does not depend on how many words a permutation consumes, so a
+    // generator thread runs ahead (mt_gen + tempering, vectorised) while the walker does only the data-dependent part
+    // (mask, compare, advance): ~0.7 ms per 524 288-element permutation instead of ~1.7 ms in one thread.
+    static constexpr int64_t kRing = 1024;       // blocks (5 KB each)
+    std::vector<MtBlock> ring;
+    std::atomic<int64_t> produced{0}, consumed{0};
+    std::atomic<bool> stop{false};
+
+    void generate() {
+        uint32_t k[kMtN];
+        std::memcpy(k, key, sizeof(k));
+        // block 0 = the caller's state as it stands (its words [pos, 624) are unconsumed); block b > 0 = mt_gen of block b - 1
+        for (int64_t b = 0;; ++b) {
+            while (b - consumed.load(std::memory_order_acquire) >= kRing) {
+                if (stop.load(std::memory_order_acquire)) return;
+                std::this_thread::yield();
+            }
+            if (stop.load(std::memory_order_acquire)) return;
+            if (b > 0) mt_gen(k);
+            MtBlock& blk = ring[(size_t)(b % kRing)];
+            std::memcpy(blk.key, k, sizeof(k));
+            mt_temper(k, blk.temp);
+            produced.store(b + 1, std::memory_order_release);
+        }
+    }
+    const MtBlock& block(int64_t b) {
+        while (produced.load(std::memory_order_acquire) <= b) std::this_thread::yield();
+        return ring[(size_t)(b % kRing)];
+    }
 
     void produce() {
+        int64_t b = 0;                 // current block
+        int p = pos;                   // next unconsumed word of it
+        const MtBlock* blk = &block(0);
         for (int r = 0; r < repeat; ++r) {
             {   // back-pressure: bounded memory (4 n bytes per pass in flight) whatever `repeat` is
                 std::unique_lock<std::mutex> lk(mu);
@@ -55,21 +100,19 @@ struct PermJob {
             }
             std::vector<uint32_t>& j = js[r];
             j.resize((size_t)(n > 0 ? n : 1));
-            int p = pos;
             // One iteration per DRAW (not per position): write the candidate, step to the next position only when it
             // is accepted (v <= i).  No data-dependent branch -- random_interval's rejection loop mispredicts ~30 % of
-            // the time when written as do/while.  The generator block is tempered in a separate (vectorisable) loop.
+            // the time when written as do/while.
             uint32_t* jd = j.data();
-            uint32_t tmp[kMtN];
             int64_t i = n - 1;
             while (i >= 1) {
-                if (p == kMtN) { mt_gen(key); p = 0; }
-                const int avail = kMtN - p;
-                for (int d = 0; d < avail; ++d) {
-                    uint32_t y = key[p + d];
-                    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-                    tmp[d] = y;
+                if (p == kMtN) {
+                    consumed.store(b + 1, std::memory_order_release);
+                    ++b; p = 0;
+                    blk = &block(b);
                 }
+                const uint32_t* tmp = blk->temp + p;
+                const int avail = kMtN - p;
                 int d = 0;
                 while (d < avail && i >= 1) {
                     // positions i in (lower, mask] share one mask: the loop-carried chain is just compare + subtract
@@ -83,10 +126,13 @@ struct PermJob {
                 }
                 p += d;
             }
-            pos = p;
             { std::lock_guard<std::mutex> lk(mu); state[r] = 1; }
             cv.notify_all();
         }
+        // final generator state = numpy's (key, pos) after these draws: the current block's key, next unconsumed word
+        std::memcpy(key, blk->key, sizeof(key));
+        pos = p;
+        stop.store(true, std::memory_order_release);
     }
     void apply_loop() {
         for (;;) {
@@ -116,7 +162,9 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
         job->pos = pos; job->n = n; job->repeat = repeat; job->out = out;
         job->js.resize((size_t)repeat);
         job->state.assign((size_t)repeat, 0);
+        job->ring.resize((size_t)PermJob::kRing);
         const int nw = n_workers < 1 ? 1 : (n_workers > repeat ? repeat : n_workers);
+        job->generator = std::thread([job] { job->generate(); });
         job->producer = std::thread([job] { job->produce(); });
         for (int w = 0; w < nw; ++w) {
             try {
@@ -128,7 +176,12 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
         }
     } catch (const std::exception& e) {     // out of memory / thread limit: the caller falls back to the serial draw
         if (job) {
+            // unblock everything before joining: the walker may be waiting on back-pressure with no worker to relieve it
+            { std::lock_guard<std::mutex> lk(job->mu); job->applied = 1 << 30; }
+            job->cv.notify_all();
             if (job->producer.joinable()) job->producer.join();
+            job->stop.store(true, std::memory_order_release);
+            if (job->generator.joinable()) job->generator.join();
             for (auto& w : job->workers) w.join();
             delete job;
         }
@@ -151,6 +204,7 @@ extern "C" int ts_host_perm_job_finish(void* handle, uint32_t* key_out, int32_t*
     PermJob* job = static_cast<PermJob*>(handle);
     TS_REQUIRE(job && key_out && pos_out, "ts_host_perm_job_finish: bad arguments");
     job->producer.join();
+    job->generator.join();
     for (auto& w : job->workers) w.join();
     std::memcpy(key_out, job->key, sizeof(job->key));
     *pos_out = job->pos;

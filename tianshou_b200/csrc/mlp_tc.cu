@@ -44,8 +44,9 @@ constexpr uint32_t cD1 = 0, cD2 = 64, cD3 = 128, cDH1 = 192, cDW2 = 256 /* 72 */
 constexpr uint32_t cT = 384, kTPart = 32;
 constexpr uint32_t kTmemCols = 512;
 
-// Optional phase timeline (diagnostics): when g_tc_timeline != nullptr, CTA 0 / thread 0 stores
-// %globaltimer at each phase boundary; read back with ts_tc_timeline().
+// Optional phase timeline (DIAGNOSTICS build only, -DTS_B200_DIAGNOSTICS -> libts_b200_diag.so): when enabled, one CTA /
+// thread 0 stores %globaltimer at each phase boundary; read back with ts_tc_timeline().  Compiled out of the product library.
+#ifdef TS_B200_DIAGNOSTICS
 __device__ unsigned long long g_tc_timeline[32];
 __device__ int g_tc_timeline_on = 0;
 __device__ int g_tc_timeline_gate = 1;      // written and read by CTA 0 / thread 0 only: which step is recorded
@@ -56,6 +57,9 @@ __device__ __forceinline__ void tstamp(int slot) {
         g_tc_timeline[slot] = t;
     }
 }
+#else
+__device__ __forceinline__ void tstamp(int) {}
+#endif
 
 
 // ---- bf16x3 operand matrices in shared memory --------------------------------------------------
@@ -755,7 +759,9 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         const int64_t tiles = (hi - lo + kRows - 1) / kRows;
         // the loss is the mean over the GLOBAL minibatch: every rank contributes hi - lo rows of its own shard
         const ppo::Scalars sc = ppo::make_scalars(hp, EPOCH ? (hi - lo) * px.world : global_rows, adv_moments ? adv_moments + 2 * m : nullptr);
+#ifdef TS_B200_DIAGNOSTICS
         if (tid == 0 && g_tc_timeline_on && (int)blockIdx.x == g_tc_timeline_on - 1) g_tc_timeline_gate = (n_mb == 1 || m == n_mb - 2);   // a step WITH barrier 3
+#endif
         tstamp(22);
         if (EPOCH && tid == 256) {    // Adam bias corrections of this step, off the critical path
             beta1_pow *= hp.beta1; beta2_pow *= hp.beta2;          // beta^(step0 + m + 1)
@@ -1245,12 +1251,14 @@ __global__ void __launch_bounds__(kThreads, 1) forward_tc_kernel(
 
 }  // namespace
 
+#ifdef TS_B200_DIAGNOSTICS
 extern "C" int ts_tc_timeline(int32_t enable, uint64_t* out32 /* host, nullable */) {
     int on = enable;
     TS_CUDA(cudaMemcpyToSymbol(g_tc_timeline_on, &on, sizeof(int)));
     if (out32) TS_CUDA(cudaMemcpyFromSymbol(out32, g_tc_timeline, 32 * sizeof(unsigned long long)));
     return 0;
 }
+#endif
 
 namespace tsb {
 bool tc_supported(const ts_actor_critic_desc& d) {

@@ -11,7 +11,7 @@ E, T = 4096, 128
 buf = VectorReplayBuffer(E * T, E, device=dev)
 fill_vector_buffer(buf, np.random.default_rng(0), E, T, 17, 6)
 algo, _, _ = build_mujoco_ppo(17, 6, dev, minibatch_shuffle="device")
-lib = _cabi.load_library()
+lib = _cabi.use_diagnostics_library()
 names = {0: "start", 1: "tile inputs staged", 2: "critic weights staged", 3: "critic fwd (3 MMA stages + 2 epi)", 4: "critic loss epi",
          16: "  c: dW3 MMA", 17: "  c: dz2 epi", 18: "  c: dW2/db2/dH1 MMA", 19: "  c: dz1 epi", 20: "  c: dW1/db1 MMA",
          5: "critic bwd done (REDs)", 6: "actor weights staged", 7: "actor fwd", 8: "actor loss epi", 9: "actor bwd done", 10: "tile loop end",

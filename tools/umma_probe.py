@@ -3,7 +3,9 @@ the error of the accumulator against an f64 matmul under both candidate lane map
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+from tianshou_b200 import _cabi
 from tianshou_b200._cabi import call, ptr, stream_ptr
+_cabi.use_diagnostics_library()      # ts_umma_selftest lives in the diagnostics build (python -m tianshou_b200.csrc.build --diag)
 
 dev = "cuda:0"
 rng = np.random.default_rng(0)

@@ -2,7 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+from tianshou_b200 import _cabi
 from tianshou_b200._cabi import call, ptr, stream_ptr
+_cabi.use_diagnostics_library()      # ts_umma_selftest lives in the diagnostics build (python -m tianshou_b200.csrc.build --diag)
 dev = "cuda:0"
 rng = np.random.default_rng(0)
 for b_mn in (0, 1):
