@@ -569,9 +569,127 @@ def main() -> None:
 
 
 def offpolicy_extras(dev) -> dict:
-    """BASELINE configs[2] / configs[3] shaped update() calls: updates/s of the device path through
-    the public API vs the torch-CPU restatement (oracle/oracle_offpolicy.py) on the same shapes.  Reduced buffer sizes (stated)."""
-    return {}
+    """BASELINE configs[2] / configs[3] shaped ``update()`` calls: updates/s of the device path through
+    the public API next to the torch-CPU restatement (oracle/oracle_offpolicy.py) on the same shapes.  Buffer sizes are reduced
+    from the 1 M / 4 M transitions BASELINE names (stated in ``workload``): the update cost does not depend on the buffer size,
+    only the host memory of the synthetic fill does."""
+    import copy
+
+    import torch
+
+    from oracle import oracle_offpolicy as oo
+    from tianshou_b200.algorithm import AdamOptimizerFactory
+    from tianshou_b200.algorithm.modelfree.dqn import DQN, DiscreteQLearningPolicy
+    from tianshou_b200.algorithm.modelfree.sac import SAC, SACPolicy
+    from tianshou_b200.data import Batch, PrioritizedVectorReplayBuffer, VectorReplayBuffer
+    from tianshou_b200.env.atari import DQNet, ScaledObsInputActionReprNet
+    from tianshou_b200.synthetic import BoxSpace
+    from tianshou_b200.utils import policy_within_training_step
+    from tianshou_b200.utils.net.common import Net
+    from tianshou_b200.utils.net.continuous import ContinuousActorProbabilistic, ContinuousCritic
+
+    out: dict = {}
+    rng = np.random.default_rng(0)
+
+    def time_updates(fn, warm: int, iters: int) -> float:
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / iters
+
+    # ---- SAC, Humanoid-shaped (obs 376, act 17, MLP[256,256], batch 256; examples/mujoco/mujoco_sac.py:29-44) ------------
+    O, A, H, B = 376, 17, (256, 256), 256
+    E, steps = 64, 1024
+    torch.manual_seed(0)
+    actor = ContinuousActorProbabilistic(preprocess_net=Net(state_shape=(O,), hidden_sizes=H), action_shape=(A,), unbounded=True,
+                                         conditioned_sigma=True).to(dev)
+    c1 = ContinuousCritic(preprocess_net=Net(state_shape=(O,), action_shape=(A,), hidden_sizes=H, concat=True)).to(dev)
+    c2 = ContinuousCritic(preprocess_net=Net(state_shape=(O,), action_shape=(A,), hidden_sizes=H, concat=True)).to(dev)
+    cpu_nets = oo.SacNets(O, A, H)
+    with torch.no_grad():
+        for dst, src in zip(cpu_nets.actor_params(), actor.parameters(), strict=True):
+            dst.copy_(src.cpu())
+        for k, c in enumerate((c1, c2)):
+            for dst, src in zip(cpu_nets.c[k].parameters(), c.parameters(), strict=True):
+                dst.copy_(src.cpu())
+    cpu_nets.c_old = [copy.deepcopy(c) for c in cpu_nets.c]
+    algo = SAC(policy=SACPolicy(actor=actor, action_space=BoxSpace(A)), policy_optim=AdamOptimizerFactory(lr=1e-3), critic=c1,
+               critic_optim=AdamOptimizerFactory(lr=1e-3), critic2=c2, critic2_optim=AdamOptimizerFactory(lr=1e-3), tau=0.005,
+               gamma=0.99, alpha=0.2, n_step_return_horizon=1)
+    buf = VectorReplayBuffer(E * steps, E, device=dev, device_mirror=True)
+    obs = rng.standard_normal((E, O)).astype(np.float32)
+    for _ in range(steps):
+        nxt = rng.standard_normal((E, O)).astype(np.float32)
+        buf.add(Batch(obs=obs, act=np.tanh(rng.standard_normal((E, A))).astype(np.float32), rew=rng.standard_normal(E),
+                      terminated=rng.random(E) < 1e-3, truncated=np.zeros(E, bool), obs_next=nxt), buffer_ids=np.arange(E))
+        obs = nxt
+    with policy_within_training_step(algo.policy):
+        dt = time_updates(lambda: algo.update(buffer=buf, sample_size=B), 5, 50)
+    host = dict(obs=np.asarray(buf.obs), act=np.asarray(buf.act), rew=np.asarray(buf.rew), done=np.asarray(buf.done),
+                terminated=np.asarray(buf.terminated), obs_next=np.asarray(buf.obs_next), offset=np.asarray(buf._extend_offset),
+                last_index=np.asarray(buf.last_index), lengths=np.asarray(buf._sizes))
+    opts = [torch.optim.Adam(cpu_nets.actor_params(), lr=1e-3)] + [torch.optim.Adam(cpu_nets.c[k].parameters(), lr=1e-3) for k in range(2)]
+
+    def cpu_sac():
+        idx = rng.integers(0, E * steps, B)
+        oo.sac_update(cpu_nets, opts, host, idx, torch.randn(B, A), torch.randn(B, A), 0.99, 1, 0.2, 0.005)
+    cpu_sac()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        cpu_sac()
+    dt_cpu = (time.perf_counter() - t0) / 20
+    out["sac"] = {"updates_per_s": 1.0 / dt, "transitions_per_s": B / dt, "ms_per_update": 1e3 * dt,
+                  "cpu_port": {"updates_per_s": 1.0 / dt_cpu, "ms_per_update": 1e3 * dt_cpu, "kind": "port (torch CPU, oracle/oracle_offpolicy.py)",
+                               "threads": torch.get_num_threads()},
+                  "workload": f"SAC.update(sample_size={B}) obs {O} act {A} MLP{list(H)} actor + 2 critics + 2 lagged critics, "
+                              f"VectorReplayBuffer {E * steps} transitions with device mirror (BASELINE configs[3] names 4 M), 1 GPU"}
+    del buf, algo
+
+    # ---- DQN, Atari-shaped (84x84x4 uint8, NatureCNN, PER, 3-step, batch 32; examples/atari/atari_dqn.py:34-49) ----------
+    Hh, Ww, NA, B = 84, 84, 6, 32
+    E, steps = 16, 2048
+    torch.manual_seed(0)
+    net = ScaledObsInputActionReprNet(DQNet(4, Hh, Ww, NA)).to(dev)
+    cpu_net = oo.nature_cnn(4, Hh, Ww, NA)
+    with torch.no_grad():
+        for dst, src in zip(cpu_net.parameters(), net.parameters(), strict=True):
+            dst.copy_(src.cpu())
+    cpu_old = copy.deepcopy(cpu_net)
+    dqn = DQN(policy=DiscreteQLearningPolicy(model=net, action_space=type("D", (), {"n": NA, "shape": ()})()), optim=AdamOptimizerFactory(lr=1e-4),
+              gamma=0.99, n_step_return_horizon=3, target_update_freq=500, is_double=True)
+    buf = PrioritizedVectorReplayBuffer(E * steps, E, alpha=0.6, beta=0.4, stack_num=4, ignore_obs_next=True, save_only_last_obs=True,
+                                        device=dev, device_mirror=True)
+    for _ in range(steps):
+        fr = rng.integers(0, 256, (E, 1, Hh, Ww), dtype=np.uint8)
+        st = np.broadcast_to(fr, (E, 4, Hh, Ww))
+        buf.add(Batch(obs=st, act=rng.integers(0, NA, E), rew=rng.standard_normal(E), terminated=rng.random(E) < 2e-3,
+                      truncated=np.zeros(E, bool), obs_next=st), buffer_ids=np.arange(E))
+    with policy_within_training_step(dqn.policy):
+        dt = time_updates(lambda: dqn.update(buffer=buf, sample_size=B), 5, 50)
+    host = dict(obs=np.asarray(buf.obs), act=np.asarray(buf.act).astype(np.int64), rew=np.asarray(buf.rew), done=np.asarray(buf.done),
+                terminated=np.asarray(buf.terminated), offset=np.asarray(buf._extend_offset), last_index=np.asarray(buf.last_index),
+                lengths=np.asarray(buf._sizes))
+    opt = torch.optim.Adam(cpu_net.parameters(), lr=1e-4)
+
+    def cpu_dqn():
+        idx = rng.integers(0, E * steps, B)
+        oo.dqn_update(cpu_net, cpu_old, opt, host, idx, np.ones(B, np.float32), 0.99, 3, True, None)
+    cpu_dqn()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        cpu_dqn()
+    dt_cpu = (time.perf_counter() - t0) / 10
+    out["dqn"] = {"updates_per_s": 1.0 / dt, "transitions_per_s": B / dt, "ms_per_update": 1e3 * dt,
+                  "cpu_port": {"updates_per_s": 1.0 / dt_cpu, "ms_per_update": 1e3 * dt_cpu, "kind": "port (torch CPU, oracle/oracle_offpolicy.py)",
+                               "threads": torch.get_num_threads()},
+                  "workload": f"DQN.update(sample_size={B}): NatureCNN on 84x84x4 uint8 frame stacks gathered from single-frame storage, "
+                              f"double DQN, 3-step return, PrioritizedVectorReplayBuffer {E * steps} frames with device mirror "
+                              "(BASELINE configs[2] names 1 M), 1 GPU"}
+    return out
 
 
 if __name__ == "__main__":

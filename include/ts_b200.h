@@ -386,23 +386,36 @@ int ts_narrow_i64_i32(const int64_t* src, int64_t n, int32_t* dst, ts_stream_t s
  * _minimize_critic_squared_loss (modelfree/ddpg.py:267-285), DQN._update_with_batch (modelfree/dqn.py:382-404)
  * and DQNet (env/atari/atari_network.py:60-122) is ONE call of ts_net_gemm (tcgen05, fp32-faithful bf16x3):
  *
- *     C[M,N] (+)= relu_mask * act( A[M,K] * B[N,K]^T + bias[N] )
+ *     C[M,N] (+)= act'(act_grad_src) * act( A[M,K] * B[N,K]^T + bias[N] )
  *
  * A / B are fp32 arrays; x_mn_major = 0: element (mn, k) at p[mn * ld + k] (k contiguous), 1: at p[k * ld + mn].
  *   forward      Y  = act(X W^T + b)   : A = X  (lda = in),  B = W  [out][in]            (0, 0)
  *   input grad   dX = (dY W) * mask    : A = dY (lda = out), B = W  as [k = out][n = in] (0, 1)
  *   weight grad  dW = dY^T X           : A = dY as [k = row][m = out] (1), B = X as [k = row][n = in] (1)
- * relu_mask (nullable): the output is zeroed where relu_mask[m * ld_mask + n] <= 0 (ReLU derivative of the layer
- * that produced A's source).  workspace (nullable): ts_net_gemm_workspace_floats(M, N, K) floats enable split-K
+ * act_grad_src (nullable): OUTPUT y of the layer whose activation derivative multiplies the result --
+ * act_grad_kind TS_ACT_RELU: * (y[m * ld_mask + n] > 0), TS_ACT_TANH: * (1 - y^2)  (back-propagation through the
+ * activation of the layer that produced this GEMM's output operand).  workspace (nullable): ts_net_gemm_workspace_floats(M, N, K) floats enable split-K
  * for long reductions with few output tiles (weight gradients); partial sums are added in a fixed order. */
 enum { TS_ACT_NONE = 0, TS_ACT_RELU = 1, TS_ACT_TANH = 2 };
 int ts_net_gemm(const float* a, int64_t lda, int32_t a_mn_major, const float* b, int64_t ldb, int32_t b_mn_major,
                 float* c, int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, int32_t act,
-                const float* relu_mask, int64_t ld_mask, int32_t accumulate, float* workspace,
+                const float* act_grad_src, int64_t ld_mask, int32_t act_grad_kind, int32_t accumulate, float* workspace,
                 int64_t workspace_floats, ts_stream_t stream);
 int64_t ts_net_gemm_workspace_floats(int32_t M, int32_t N, int32_t K);
 /* out[n] (+)= sum_m x[m * ld + n]  (bias gradients) */
 int ts_net_colsum(const float* x, int64_t ld, int32_t M, int32_t N, float* out, int32_t accumulate, ts_stream_t stream);
+
+/* PPO / A2C loss rows between the forward and backward GEMMs of a layered actor-critic (ppo.py:179-216, a2c.py:262-270):
+ * head [B][A] = mu (Gaussian, sigma = exp(logstd[A])) or logits (categorical: Categorical(probs = softmax(logits)),
+ * utils/net/discrete.py:69-92), value [B].  logp_out [B] always; with dhead != NULL also dhead [B][A], dvalue [B],
+ * dlogstd_rows [B][A] (Gaussian, nullable), loss_rows [B][3] = (surrogate objective, value loss, entropy).
+ * act: [B][A] (Gaussian) or [B] float-coded indices (categorical). */
+int ts_ppo_rows(const float* head, const float* value, const float* logstd, const float* act, const float* adv,
+                const float* ret, const float* logp_old, const float* v_s, int64_t B, int32_t A, int32_t categorical,
+                const ts_ppo_hparams* hp, int64_t global_rows, const float* adv_moments, float* logp_out, float* dhead,
+                float* dvalue, float* dlogstd_rows, float* loss_rows, ts_stream_t stream);
+/* stats row (loss, actor loss, vf loss, entropy, -, rows) from loss_rows */
+int ts_ppo_rows_stats(const float* loss_rows, int64_t B, const ts_ppo_hparams* hp, float* stats_row, ts_stream_t stream);
 
 /* Frame stacking on the device (ReplayBuffer.get, data/buffer/buffer_base.py:557-603): out[i][s] for s = 0..S-1 is
  * the slot of the s-th oldest frame of the stacked observation of index[i] (out[i][S-1] = index[i], each earlier

@@ -11,12 +11,12 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _gemm(a, lda, a_mn, b, ldb, b_mn, c, M, N, K, bias=None, act=0, mask=None, accumulate=False, split=True):
+def _gemm(a, lda, a_mn, b, ldb, b_mn, c, M, N, K, bias=None, act=0, mask=None, mask_kind=1, accumulate=False, split=True):
     from tianshou_b200._cabi import call, load_library, ptr, stream_ptr
     ws_n = int(load_library().ts_net_gemm_workspace_floats(M, N, K)) if split else 0
     ws = torch.empty(max(ws_n, 1), dtype=torch.float32, device=DEV)
     call("ts_net_gemm", ptr(a), lda, a_mn, ptr(b), ldb, b_mn, ptr(c), c.shape[1], M, N, K, ptr(bias), act,
-         ptr(mask), mask.shape[1] if mask is not None else 0, int(accumulate), ptr(ws) if ws_n else None, ws_n, stream_ptr())
+         ptr(mask), mask.shape[1] if mask is not None else 0, mask_kind, int(accumulate), ptr(ws) if ws_n else None, ws_n, stream_ptr())
     return ws_n
 
 
@@ -47,6 +47,10 @@ def test_net_gemm_input_gradient_arrangement(M, N, K):
     _gemm(dy, K, 0, w, N, 1, out, M, N, K, mask=src)
     ref = (dy.double() @ w.double()) * (src > 0)
     record_parity(f"net_gemm_dx/{M}x{N}x{K}", out.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6, atol=2e-6 * float(ref.abs().max()))
+    y = torch.tanh(src)
+    _gemm(dy, K, 0, w, N, 1, out, M, N, K, mask=y, mask_kind=2)
+    ref = (dy.double() @ w.double()) * (1 - y.double() ** 2)
+    record_parity(f"net_gemm_dx_tanh/{M}x{N}x{K}", out.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6, atol=2e-6 * float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("rows,out_f,in_f", [(256, 256, 393), (12800, 32, 256), (32, 512, 3136), (77, 6, 20)])

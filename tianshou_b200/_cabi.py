@@ -101,7 +101,9 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
     "ts_narrow_i64_i32": [_P, _I64, _P, _P],
     # layered networks of the off-policy algorithms (net_gemm.cu / net_ops.cu)
-    "ts_net_gemm": [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I64, _I32, _P, _I64, _P],
+    "ts_net_gemm": [_P, _I64, _I32, _P, _I64, _I32, _P, _I64, _I32, _I32, _I32, _P, _I32, _P, _I64, _I32, _I32, _P, _I64, _P],
+    "ts_ppo_rows": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P, _P, _P, _P, _P],
+    "ts_ppo_rows_stats": [_P, _I64, _P, _P, _P],
     "ts_net_colsum": [_P, _I64, _I32, _I32, _P, _I32, _P],
     "ts_stack_prev_indices": [_P, _I64, _I32, _P, _I64, _P, _P, _P, _P, _P],
     "ts_im2col_u8": [_P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _D, _P, _P],

@@ -70,28 +70,50 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         if not optim_include_actor:
             raise UnsupportedModelError("critic-only optimizers (optim_include_actor=False) are not fused yet")
         self._actor_critic = ActorCritic(self.policy.actor, self.critic)
-        # kernel-side view of the networks: validate structure, flatten parameters
-        self._desc, plist = describe_actor_critic(self.policy.actor, self.critic)
+        # kernel-side view of the networks: validate structure, flatten parameters.  Shapes outside the fused kernels' envelope
+        # (two 64-wide layers, obs <= 64) run layer by layer on the tensor-core GEMM (algorithm/layered.py); anything that is
+        # not a Linear / ReLU | Tanh actor-critic raises -- there is no eager-PyTorch path.
+        self._layered = None
+        try:
+            import os as _os
+            if _os.environ.get("TS_B200_FORCE_LAYERED", "0") == "1":      # tests: run the layer-wise path on any shape
+                raise UnsupportedModelError("TS_B200_FORCE_LAYERED=1")
+            self._desc, plist = describe_actor_critic(self.policy.actor, self.critic)
+        except UnsupportedModelError as fused_err:
+            from ..layered import try_layered
+            try:
+                self._layered = try_layered(self.policy.actor, self.critic)
+            except UnsupportedModelError as layered_err:
+                raise UnsupportedModelError(f"{fused_err}; layer-wise path: {layered_err}") from layered_err
+            self._desc, plist = None, self._layered.group.params
         dev = plist[0].device
         if dev.type != "cuda":
             raise UnsupportedModelError(
                 f"actor/critic live on {dev}; tianshou_b200 has no CPU path -- move them to a CUDA device first")
-        if self._desc.flags & AC_CATEGORICAL:
-            check_categorical_dist_fn(self.policy.dist_fn, self._desc.act_dim, dev)
+        categorical = self._layered.categorical if self._layered is not None else bool(self._desc.flags & AC_CATEGORICAL)
+        act_dim = self._layered.act_dim if self._layered is not None else self._desc.act_dim
+        if categorical:
+            check_categorical_dist_fn(self.policy.dist_fn, act_dim, dev)
         else:
-            check_gaussian_dist_fn(self.policy.dist_fn, self._desc.act_dim, dev)
-        self._flat = FlatParams(plist, dev, GRAD_EXTRA)
-        # scratch for the pre-split (bf16x3) weight image of the tensor-core update kernel; None -> the
-        # kernels gather + split the weights themselves (networks the tensor-core path does not cover)
-        import ctypes as _C
-        from ..._cabi import load_library
-        nbytes = int(load_library().ts_ppo_weight_image_bytes(_C.byref(self._desc)))
-        self._flat.weight_image = torch.zeros(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
-        if hasattr(self.policy, "_fused_inference"):      # Collector-side inference through the same forward kernel
-            self.policy._fused_inference = (self._flat, self._desc)
-        if self._world_size() > 1 and getattr(self, "data_parallel", True):  # replicas start bit-identical
-            from ...parallel import broadcast_params_
-            broadcast_params_(self._flat.flat)
+            check_gaussian_dist_fn(self.policy.dist_fn, act_dim, dev)
+        if self._layered is not None:
+            if self._world_size() > 1 and getattr(self, "data_parallel", True):
+                raise UnsupportedModelError("the layer-wise actor-critic path is single-GPU")
+            self._flat = self._layered.group
+            self._flat.weight_image = None
+        else:
+            self._flat = FlatParams(plist, dev, GRAD_EXTRA)
+            # scratch for the pre-split (bf16x3) weight image of the tensor-core update kernel; None -> the
+            # kernels gather + split the weights themselves (networks the tensor-core path does not cover)
+            import ctypes as _C
+            from ..._cabi import load_library
+            nbytes = int(load_library().ts_ppo_weight_image_bytes(_C.byref(self._desc)))
+            self._flat.weight_image = torch.zeros(nbytes, dtype=torch.uint8, device=dev) if nbytes > 0 else None
+            if hasattr(self.policy, "_fused_inference"):      # Collector-side inference through the same forward kernel
+                self.policy._fused_inference = (self._flat, self._desc)
+            if self._world_size() > 1 and getattr(self, "data_parallel", True):  # replicas start bit-identical
+                from ...parallel import broadcast_params_
+                broadcast_params_(self._flat.flat)
         # a real torch Adam (+ scheduler) keeps lr schedules and state_dict round trips unchanged
         self.optim = self._create_optimizer(self._actor_critic, optim, max_grad_norm=max_grad_norm)
         adam_hyperparams(self.optim._optim)  # validates optimizer family early
@@ -132,10 +154,13 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
                                         "by the MLP actor-critic kernels")
         obs_w = int(np.prod(meta_host.obs.shape[1:], dtype=np.int64))
         act_w = int(np.prod(meta_host.act.shape[1:], dtype=np.int64))
-        want_act = 1 if self._desc.flags & AC_CATEGORICAL else int(self._desc.act_dim)
-        if obs_w != int(self._desc.obs_dim) or act_w != want_act:
+        if self._layered is not None:
+            net_obs, want_act = self._layered.obs_dim, (1 if self._layered.categorical else self._layered.act_dim)
+        else:
+            net_obs, want_act = int(self._desc.obs_dim), (1 if self._desc.flags & AC_CATEGORICAL else int(self._desc.act_dim))
+        if obs_w != net_obs or act_w != want_act:
             raise ValueError(f"buffer rows (obs width {obs_w}, act width {act_w}) do not match the networks "
-                             f"(obs_dim {int(self._desc.obs_dim)}, action width {want_act})")
+                             f"(obs_dim {net_obs}, action width {want_act})")
         n = len(buffer)
         full = n == buffer.maxsize and bool(np.all(buffer._ins == 0))
         need = ("obs", "act", "rew", "terminated", "truncated", "done") + (("obs_next",) if buffer._save_obs_next else ())
@@ -182,7 +207,11 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         n = batch.obs.shape[0]
         v_s = self._buf("v_s", n, torch.float32)
         v_next = self._buf("v_next", n, torch.float32)
-        ops.critic_forward(self._flat.flat, self._desc, batch.obs, batch.obs_next, out=v_s, out2=v_next)
+        if self._layered is not None:
+            self._layered.critic_values(batch.obs, v_s)
+            self._layered.critic_values(batch.obs_next, v_next)
+        else:
+            ops.critic_forward(self._flat.flat, self._desc, batch.obs, batch.obs_next, out=v_s, out2=v_next)
         rms = self._rms_device() if self.return_scaling else None
         adv = self._buf("adv", n, torch.float32)
         ret = self._buf("returns", n, torch.float32)

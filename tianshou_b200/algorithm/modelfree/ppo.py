@@ -110,6 +110,12 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
     # ------------------------------------------------------------------ update
     def _update_with_batch(self, batch: Batch, batch_size: int | None, repeat: int) -> A2CTrainingStats:
         """The repeat x minibatch loop of ppo.py:164-224 as device work."""
+        if self._layered is not None:        # networks outside the fused kernels' envelope: layer-wise tensor-core path
+            from ..layered import layered_update
+            result = self._stats_from_device(layered_update(self, batch, batch_size, repeat))
+            self._rms_end()
+            self._flat.export_state(self.optim._optim)
+            return result
         dev = self.device
         N = batch.obs.shape[0]
         size = batch_size or N
@@ -293,7 +299,10 @@ class PPO(FusedActorCriticUpdate):
         batch = self._add_returns_and_advantages(batch, buffer, indices)
         n = batch.obs.shape[0]
         logp_old = self._buf("logp_old", n, torch.float32)
-        ops.actor_logp(self._flat.flat, self._desc, batch.obs, batch.act, out=logp_old)
+        if self._layered is not None:
+            self._layered.actor_logp(batch.obs, batch.act, logp_old, self._loss_hparams())
+        else:
+            ops.actor_logp(self._flat.flat, self._desc, batch.obs, batch.act, out=logp_old)
         batch.__dict__["logp_old"] = logp_old
         return batch
 

@@ -124,7 +124,9 @@ class _Layer:
 def _activation_code(m: nn.Module) -> int:
     if type(m) is nn.ReLU:
         return ACT_RELU
-    raise UnsupportedModelError(f"fused layered networks support ReLU activations only, got {m}")
+    if type(m) is nn.Tanh:
+        return ACT_TANH
+    raise UnsupportedModelError(f"fused layered networks support ReLU / Tanh activations only, got {m}")
 
 
 def compile_sequential(mods: list[nn.Module], input_shape: tuple[int, ...]) -> list[_Layer]:
@@ -203,10 +205,10 @@ class FusedStack:
         return t
 
     def _gemm(self, a, lda, a_mn, b, ldb, b_mn, c, ldc, M, N, K, bias=None, act=ACT_NONE, mask=None, ld_mask=0,
-              accumulate=False) -> None:
+              mask_kind=ACT_RELU, accumulate=False) -> None:
         ws_n = int(self._lib.ts_net_gemm_workspace_floats(M, N, K))
         ws = self._buf(("ws",), ws_n) if ws_n > 0 else None
-        call("ts_net_gemm", a, lda, a_mn, b, ldb, b_mn, c, ldc, M, N, K, bias, act, mask, ld_mask, int(accumulate),
+        call("ts_net_gemm", a, lda, a_mn, b, ldb, b_mn, c, ldc, M, N, K, bias, act, mask, ld_mask, int(mask_kind), int(accumulate),
              ptr(ws) if ws is not None else None, ws_n, stream_ptr(self.device))
 
     def _w(self, L: _Layer, flat: torch.Tensor | None = None) -> int:
@@ -255,55 +257,73 @@ class FusedStack:
 
     # ------------------------------------------------------------------ backward
     def backward(self, acts: list[torch.Tensor], dy: torch.Tensor, rows: int, tag: str = "a", *, param_grads: bool = True,
-                 input_grad: bool = False, input_cols: tuple[int, int] | None = None) -> torch.Tensor | None:
-        """Back-propagate ``dy`` (gradient w.r.t. the LAST layer's output; its activation must be none).  Weight / bias
-        gradients are STORED into the group's gradient buffer (``zero_grad`` + ``backward`` of algorithm_base.py:497-498).
-        Returns d loss / d input (columns ``input_cols`` of the first Linear's input) if ``input_grad``."""
+                 input_grad: bool = False, input_cols: tuple[int, int] | None = None, dy_preact: bool = False,
+                 input_act: tuple[int, torch.Tensor] | None = None, dx_out: torch.Tensor | None = None,
+                 dx_accumulate: bool = False, grad_accumulate: bool = False) -> torch.Tensor | None:
+        """Back-propagate ``dy`` = gradient w.r.t. the LAST layer's output (its activation must be none, or ``dy_preact``: the
+        caller already folded the last activation's derivative in).  Weight / bias gradients are STORED into the group's
+        gradient buffer (``zero_grad`` + ``backward`` of algorithm_base.py:497-498) or added with ``grad_accumulate`` (a trunk
+        shared by two losses).  With ``input_grad`` returns d loss / d input (columns ``input_cols`` of the first Linear's
+        input), multiplied by the derivative of the activation ``input_act = (kind, y)`` that produced this stack's input (a
+        head on top of a trunk), written to / accumulated into ``dx_out`` when given."""
         g = self.group
         st = stream_ptr(self.device)
         n = len(self.layers)
-        if self.layers[-1].act != ACT_NONE:
+        if self.layers[-1].act != ACT_NONE and not dy_preact:
             raise UnsupportedModelError("backward expects a linear output layer")
         dz = dy                                   # gradient w.r.t. the pre-activation of layer i (mask already applied)
         for i in range(n - 1, -1, -1):
             L = self.layers[i]
             x_in = acts[i]
-            prev_relu = i > 0 and self._producer_act(i) == ACT_RELU
+            prev_act = self._producer_act(i) if i > 0 else (input_act[0] if input_act is not None else ACT_NONE)
+            act_src = x_in if i > 0 else (input_act[1] if input_act is not None else None)
             need_dx = i > 0 or input_grad
+            acc = int(grad_accumulate)
             if L.kind == "linear":
                 M_rows = rows
                 if param_grads:
                     gw = g.grad.data_ptr() + 4 * g.offset(L.weight)
                     gb = g.grad.data_ptr() + 4 * g.offset(L.bias)
-                    self._gemm(ptr(dz), L.out_dim, 1, ptr(x_in), L.in_dim, 1, gw, L.in_dim, L.out_dim, L.in_dim, M_rows)
-                    call("ts_net_colsum", ptr(dz), L.out_dim, M_rows, L.out_dim, gb, 0, st)
+                    self._gemm(ptr(dz), L.out_dim, 1, ptr(x_in), L.in_dim, 1, gw, L.in_dim, L.out_dim, L.in_dim, M_rows,
+                               accumulate=grad_accumulate)
+                    call("ts_net_colsum", ptr(dz), L.out_dim, M_rows, L.out_dim, gb, acc, st)
                 if need_dx:
                     lo, hi = (0, L.in_dim) if (i > 0 or input_cols is None) else input_cols
                     width = hi - lo
-                    dx = self._buf((tag, "dx", i), M_rows * width)[: M_rows * width].view(M_rows, width)
-                    mask = ptr(x_in) if prev_relu else None
+                    if i == 0 and dx_out is not None:
+                        dx = dx_out
+                    else:
+                        dx = self._buf((tag, "dx", i), M_rows * width)[: M_rows * width].view(M_rows, width)
+                    mask = ptr(act_src) if prev_act != ACT_NONE else None
                     self._gemm(ptr(dz), L.out_dim, 0, self._w(L) + 4 * lo, L.in_dim, 1, ptr(dx), width, M_rows, width, L.out_dim,
-                               mask=mask, ld_mask=L.in_dim)
+                               mask=mask, ld_mask=L.in_dim, mask_kind=prev_act if prev_act != ACT_NONE else ACT_RELU,
+                               accumulate=(i == 0 and dx_accumulate))
                     dz = dx
             elif L.kind == "conv":
+                if prev_act == ACT_TANH:
+                    raise UnsupportedModelError("tanh in front of a convolution is not supported")
                 R = rows * L.Ho * L.Wo
                 col = self._bufs[(tag, "col", i)][: R * L.in_dim].view(R, L.in_dim)
                 if param_grads:
                     gw = g.grad.data_ptr() + 4 * g.offset(L.weight)
                     gb = g.grad.data_ptr() + 4 * g.offset(L.bias)
-                    self._gemm(ptr(dz), L.out_dim, 1, ptr(col), L.in_dim, 1, gw, L.in_dim, L.out_dim, L.in_dim, R)
-                    call("ts_net_colsum", ptr(dz), L.out_dim, R, L.out_dim, gb, 0, st)
+                    self._gemm(ptr(dz), L.out_dim, 1, ptr(col), L.in_dim, 1, gw, L.in_dim, L.out_dim, L.in_dim, R,
+                               accumulate=grad_accumulate)
+                    call("ts_net_colsum", ptr(dz), L.out_dim, R, L.out_dim, gb, acc, st)
                 if i > 0:
                     dcol = self._buf((tag, "dcol", i), R * L.in_dim)[: R * L.in_dim].view(R, L.in_dim)
                     self._gemm(ptr(dz), L.out_dim, 0, self._w(L), L.in_dim, 1, ptr(dcol), L.in_dim, R, L.in_dim, L.out_dim)
                     dx = self._buf((tag, "dx", i), rows * L.H * L.W * L.C)[: rows * L.H * L.W * L.C]
-                    call("ts_col2im_f32", ptr(dcol), rows, L.C, L.H, L.W, L.k, L.s, ptr(x_in) if prev_relu else None, ptr(dx), st)
+                    call("ts_col2im_f32", ptr(dcol), rows, L.C, L.H, L.W, L.k, L.s, ptr(x_in) if prev_act == ACT_RELU else None,
+                         ptr(dx), st)
                     dz = dx
                 elif input_grad:
                     raise UnsupportedModelError("input gradients through the first convolution are not provided")
             else:  # flatten: NCHW-flat gradient back to NHWC rows (+ the producer's ReLU mask)
+                if prev_act == ACT_TANH:
+                    raise UnsupportedModelError("tanh in front of a flatten is not supported")
                 dx = self._buf((tag, "dx", i), rows * L.out_dim)[: rows * L.out_dim]
-                call("ts_nchw_flat_to_nhwc", ptr(dz), rows, L.H * L.W, L.C, ptr(x_in) if prev_relu else None, ptr(dx), st)
+                call("ts_nchw_flat_to_nhwc", ptr(dz), rows, L.H * L.W, L.C, ptr(x_in) if prev_act == ACT_RELU else None, ptr(dx), st)
                 dz = dx
         return dz if input_grad else None
 

@@ -660,6 +660,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
     __shared__ __align__(8) uint64_t s_wbar;
     __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
     __shared__ int32_t s_row[kRows];
+    __shared__ float s_part[4][128];      // actor loss epilogue: log-prob partials of the 4 action groups; optimiser half: fold partials
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int P = (int)gridDim.x;
     const int64_t width = d.n_params + TS_PPO_GRAD_EXTRA;
@@ -744,8 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         chunk_store(sm0, S.X, kRows, S.KXP, in.xv);
         if (tid < kRows) {
 #pragma unroll
-            for (int a = 0; a < kMaxAct; a += 4)
-                *reinterpret_cast<float4*>(actt + tid * kMaxAct + a) = make_float4(in.av[a], in.av[a + 1], in.av[a + 2], in.av[a + 3]);
+            for (int a = 0; a < kMaxAct; ++a) actt[a * kRows + tid] = in.av[a];      // [a][r]: rows on consecutive banks
             rowv[tid] = in.rv[0]; rowv[kRows + tid] = in.rv[1]; rowv[2 * kRows + tid] = in.rv[2]; rowv[3 * kRows + tid] = in.rv[3];
         }
     };
@@ -779,6 +779,18 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             }
             staged = false;
 
+            // dataset rows of this CTA's NEXT tile: the (DRAM-latency) load of the permutation entry is issued here and
+            // committed to s_row after the critic pass -- s_row itself was consumed by load_inputs above / one step ago
+            int32_t next_row = 0;
+            int next_kind = 0;                                   // 1: next tile of this minibatch, 2: first tile of the next one
+            if (t + P < tiles) next_kind = 1;
+            else if (m + 1 < n_mb && (int64_t)blockIdx.x < mb_tiles(m + 1)) next_kind = 2;
+            if (next_kind != 0 && tid < kRows) {
+                const int mm = next_kind == 1 ? m : m + 1;
+                const int64_t pos = mb_lo(mm) + (next_kind == 1 ? t + P : (int64_t)blockIdx.x) * kRows + tid;
+                next_row = pos < mb_hi(mm) ? (perm ? __ldg(perm + pos) : (int32_t)pos) : 0;
+            }
+
             // ================= critic ================================================================
             float h1[kCols], h2[kCols];
             tstamp(1);
@@ -807,50 +819,63 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             tstamp(5);
             __syncthreads();
             if (tid == 0) out_acc(grad + gc.b3, (red[0] + red[1]) + (red[2] + red[3]), first);
-            // row ids of this CTA's next tile (s_row was consumed by load_inputs long ago)
-            if (t + P < tiles) prefetch_rows(m, t + P);
-            else if (m + 1 < n_mb && (int64_t)blockIdx.x < mb_tiles(m + 1)) { prefetch_rows(m + 1, blockIdx.x); next_rows_ready = true; }
+            // row ids of this CTA's next tile (loaded at the top of the tile; s_row was consumed by load_inputs long ago)
+            if (next_kind != 0 && tid < kRows) s_row[tid] = next_row;
+            if (next_kind == 2) next_rows_ready = true;
 
             // ================= actor =================================================================
             wait_weights(ga, A);
             tstamp(6);
             trunk_forward(sm, sm0, S, tmem, pipe, h1, h2);
             tstamp(7);
+            // Actor loss epilogue on all 16 warps: thread (row r = 32 q + lane, group cq) owns the actions a = cq + 4 u -- the
+            // four groups' log-prob partials meet in shared memory, every thread then evaluates the row's surrogate and writes
+            // dOut / column sums of ITS actions only (the 128-thread version was a 2 us dependent chain on one warp per scheduler).
             float clip_row = 0.0f;
-            if (tid < kRows) {
-                const int r = tid;
-                float v16[16], cs[32];      // cs[a] = d/d mu_a, cs[16 + a] = d/d logstd_a
-                umma::tmem_ld16(tmem + ((32u * warp) << 16) + cD3, v16);
+            {
+                const int q = warp & 3, cq = warp >> 2;
+                const int r = 32 * q + lane;
                 const float* b3 = reinterpret_cast<const float*>(sm + S.b3);
                 const float* inv_var = red + 64;      // 1 / sigma^2
                 const float* logc = red + 80;         // log sigma + log sqrt(2 pi)
-                float lp = 0.0f;
-                float diff[kMaxAct], d2v[kMaxAct];
+                float diff[4], d2v[4];
+                float lpp = 0.0f;
 #pragma unroll
-                for (int a4 = 0; a4 < kMaxAct; a4 += 4) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(actt + r * kMaxAct + a4);
-                    const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int a = a4 + u;
-                        diff[a] = 0.0f; d2v[a] = 0.0f;
-                        if (a < A) {     // warp-uniform
-                            diff[a] = xs[u] - (v16[a] + b3[a]);
-                            d2v[a] = diff[a] * diff[a] * inv_var[a];
-                            lp += fmaf(-0.5f, d2v[a], -logc[a]);   // log N(x; mu, sigma)
-                        }
+                for (int u = 0; u < 4; ++u) {
+                    const int a = cq + 4 * u;
+                    diff[u] = 0.0f; d2v[u] = 0.0f;
+                    if (a < A) {     // warp-uniform
+                        const float mu = umma::tmem_ld1(tmem + ((32u * q) << 16) + cD3 + (uint32_t)a) + b3[a];
+                        diff[u] = actt[a * kRows + r] - mu;
+                        d2v[u] = diff[u] * diff[u] * inv_var[a];
+                        lpp += fmaf(-0.5f, d2v[u], -logc[a]);      // log N(x; mu, sigma)
                     }
                 }
-                float gl = 0.0f;
-                if (r < nrows) ppo::actor_row(sc, lp, rowv[2 * kRows + r], rowv[r], clip_row, gl);
+                s_part[cq][r] = lpp;
+                __syncthreads();
+                const float lp = (s_part[0][r] + s_part[1][r]) + (s_part[2][r] + s_part[3][r]);
+                float gl = 0.0f, obj = 0.0f;
+                if (r < nrows) ppo::actor_row(sc, lp, rowv[2 * kRows + r], rowv[r], obj, gl);
+                if (cq == 0) clip_row = obj;          // one group carries the row's objective into the loss sum
+                float* dof = reinterpret_cast<float*>(sm + S.dof);
 #pragma unroll
-                for (int a = 0; a < kMaxAct; ++a) {
-                    cs[a] = a < A ? gl * diff[a] * inv_var[a] : 0.0f;
-                    cs[16 + a] = a < A ? gl * (d2v[a] - 1.0f) : 0.0f;
+                for (int u = 0; u < 4; ++u) {
+                    const int a = cq + 4 * u;
+                    if (a < A) {     // warp-uniform
+                        const float g_mu = gl * diff[u] * inv_var[a];          // d loss / d mu_a
+                        const float g_ls = gl * (d2v[u] - 1.0f);               // d loss / d logstd_a
+                        dof[a * kRows + r] = g_mu;
+                        uint32_t w0, w1, w2;
+                        split3_pair(g_mu, 0.0f, w0, w1, w2);
+                        uint8_t* pdo = sm0 + (S.DO.base + moff((uint32_t)r, (uint32_t)a, S.DO.RS));   // columns >= A stay zero (critic pass)
+                        *reinterpret_cast<uint16_t*>(pdo) = (uint16_t)w0;
+                        *reinterpret_cast<uint16_t*>(pdo + S.DO.part) = (uint16_t)w1;
+                        *reinterpret_cast<uint16_t*>(pdo + 2 * S.DO.part) = (uint16_t)w2;
+                        // column sums over the 32 rows of this warp: red[128 + 32 q + a] <- db3[a], red[128 + 32 q + 16 + a] <- dlogstd[a]
+                        const float s_mu = warp_sum(g_mu), s_ls = warp_sum(g_ls);
+                        if (lane == 0) { red[128 + 32 * q + a] = s_mu; red[128 + 32 * q + 16 + a] = s_ls; }
+                    }
                 }
-                write_dout_row(sm, sm0, S, r, cs);
-                // column sums over the 32 rows of this warp: lane a <- db3[a], lane 16 + a <- dlogstd[a]
-                red[128 + 32 * warp + lane] = warp_transpose_sum32(cs);
             }
             tstamp(8);
             trunk_backward(sm, sm0, S, tmem, pipe, ga, d.obs_dim, A, grad, h1, h2, first, [] {});
@@ -880,7 +905,6 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         if (!EPOCH) break;
 
         // ---- optimiser half of the step --------------------------------------------------------------
-        __shared__ float s_part[4][128];
         __shared__ double s_red[4];
         const int Pm = (int)tsb::imin((int64_t)P, tiles);           // partial rows written for this minibatch
         const int64_t slice = (width + P - 1) / P;

@@ -39,8 +39,9 @@ struct GemmParams {
     int M, N, K;
     const float* bias;   // [N], nullable
     int act;             // TS_ACT_*
-    const float* mask;   // nullable: multiply by (mask[m * ld_mask + n] > 0)  -- ReLU backward of the PRODUCER layer
-    int64_t ld_mask;
+    const float* mask;   // nullable: activation derivative of the PRODUCER layer from its OUTPUT y = mask[m * ld_mask + n]:
+    int64_t ld_mask;     //   mask_kind TS_ACT_RELU: x * (y > 0) ;  TS_ACT_TANH: x * (1 - y^2)
+    int mask_kind;
     int accumulate;      // C += result
     int splits;          // split-K factor (grid.z); partials are reduced by splitk_reduce_kernel
     int k_per_split;     // multiple of BK
@@ -126,6 +127,9 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_base, in
     __syncwarp();
 }
 
+__device__ __forceinline__ float apply_act_grad(float x, float y, int kind) {
+    return kind == TS_ACT_TANH ? x * fmaf(-y, y, 1.0f) : (y > 0.0f ? x : 0.0f);
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == TS_ACT_RELU) return fmaxf(x, 0.0f);
     if (act == TS_ACT_TANH) return tanhf(x);
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_gemm_kernel(const GemmParams 
                     if (!plain) {
                         if (P.bias) x += __ldg(P.bias + n);
                         x = apply_act(x, P.act);
-                        if (P.mask) x = __ldg(P.mask + (int64_t)m * P.ld_mask + n) > 0.0f ? x : 0.0f;
+                        if (P.mask) x = apply_act_grad(x, __ldg(P.mask + (int64_t)m * P.ld_mask + n), P.mask_kind);
                         if (P.accumulate) x += *dst;
                     }
                     *dst = x;
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) net_gemm_kernel(const GemmParams 
 // C (+)= epilogue( sum_z partial[z] ), fixed summation order (deterministic)
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, float* __restrict__ c, int64_t ldc, int M, int N,
                                      const float* __restrict__ bias, int act, const float* __restrict__ mask, int64_t ld_mask,
-                                     int accumulate) {
+                                     int mask_kind, int accumulate) {
     const int64_t total = (int64_t)M * N;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int m = (int)(e / N), n = (int)(e - (int64_t)m * N);
@@ -228,7 +232,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
         for (int z = 0; z < splits; ++z) x += part[(int64_t)z * total + e];
         if (bias) x += __ldg(bias + n);
         x = apply_act(x, act);
-        if (mask) x = __ldg(mask + (int64_t)m * ld_mask + n) > 0.0f ? x : 0.0f;
+        if (mask) x = apply_act_grad(x, __ldg(mask + (int64_t)m * ld_mask + n), mask_kind);
         float* dst = c + (int64_t)m * ldc + n;
         if (accumulate) x += *dst;
         *dst = x;
@@ -272,7 +276,7 @@ size_t net_gemm_workspace_floats(int M, int N, int K, int* splits_out) {
 }
 
 int net_gemm(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb, int b_mn, float* c, int64_t ldc, int M, int N,
-             int K, const float* bias, int act, const float* mask, int64_t ld_mask, int accumulate, float* workspace,
+             int K, const float* bias, int act, const float* mask, int64_t ld_mask, int mask_kind, int accumulate, float* workspace,
              size_t workspace_floats, cudaStream_t st) {
     static bool configured[kMaxDevices] = {};
     const int dev = device_ordinal();
@@ -285,7 +289,7 @@ int net_gemm(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb,
     P.a = Operand{a, lda, a_mn, M};
     P.b = Operand{b, ldb, b_mn, N};
     P.c = c; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
-    P.bias = bias; P.act = act; P.mask = mask; P.ld_mask = ld_mask; P.accumulate = accumulate;
+    P.bias = bias; P.act = act; P.mask = mask; P.ld_mask = ld_mask; P.mask_kind = mask_kind; P.accumulate = accumulate;
     int splits = 1;
     const size_t need = net_gemm_workspace_floats(M, N, K, &splits);
     if (splits > 1 && (workspace == nullptr || workspace_floats < need)) splits = 1;     // no room: run unsplit
@@ -303,7 +307,7 @@ int net_gemm(const float* a, int64_t lda, int a_mn, const float* b, int64_t ldb,
     if (splits > 1) {
         const int64_t total = (int64_t)M * N;
         splitk_reduce_kernel<<<(unsigned)imin((total + 255) / 256, 148 * 8), 256, 0, st>>>(workspace, splits, c, ldc, M, N, bias, act,
-                                                                                           mask, ld_mask, accumulate);
+                                                                                           mask, ld_mask, mask_kind, accumulate);
         if (check_launch("ts_net_gemm/splitk")) return 1;
     }
     return 0;
@@ -319,11 +323,12 @@ int net_colsum(const float* x, int64_t ld, int M, int N, float* out, int accumul
 
 extern "C" int ts_net_gemm(const float* a, int64_t lda, int32_t a_mn_major, const float* b, int64_t ldb, int32_t b_mn_major,
                            float* c, int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, int32_t act,
-                           const float* relu_mask, int64_t ld_mask, int32_t accumulate, float* workspace,
+                           const float* act_grad_src, int64_t ld_mask, int32_t act_grad_kind, int32_t accumulate, float* workspace,
                            int64_t workspace_floats, ts_stream_t stream) {
     TS_REQUIRE(a && b && c && M >= 0 && N >= 0 && K >= 0, "ts_net_gemm: null pointer / negative size");
     TS_REQUIRE(act >= TS_ACT_NONE && act <= TS_ACT_TANH, "ts_net_gemm: unknown activation %d", act);
-    return tsb::net_gemm(a, lda, a_mn_major, b, ldb, b_mn_major, c, ldc, M, N, K, bias, act, relu_mask, ld_mask, accumulate,
+    TS_REQUIRE(!act_grad_src || act_grad_kind == TS_ACT_RELU || act_grad_kind == TS_ACT_TANH, "ts_net_gemm: unknown act_grad_kind %d", act_grad_kind);
+    return tsb::net_gemm(a, lda, a_mn_major, b, ldb, b_mn_major, c, ldc, M, N, K, bias, act, act_grad_src, ld_mask, act_grad_kind, accumulate,
                          workspace, (size_t)(workspace_floats > 0 ? workspace_floats : 0), tsb::as_stream(stream));
 }
 
