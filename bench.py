@@ -255,6 +255,9 @@ def main() -> None:
     ap.add_argument("--envs", type=int, default=0, help="override the config's env count (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip config4 / ingest / off-policy extras")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="after the warm-up run ONE end-to-end update() between cudaProfilerStart/Stop and exit (for "
+                         "`ncu --profile-from-start off ...`: the launch list of exactly the timed step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -338,6 +341,17 @@ def main() -> None:
 
         def e2e_step(a=algo):
             a.update(buffer=buf, batch_size=BS, repeat=REPEAT)
+
+        if args.profile_one_step:
+            for _ in range(W):
+                e2e_step()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            e2e_step()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            print(json.dumps({"profiled": "one e2e update()", "config": workload_config(world, args.config, args.scaling)}))
+            return
 
         # ---- headline: the DEFAULT public API (reference-exact minibatch order) ------------------------------
         for _ in range(W):

@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -50,7 +51,7 @@ struct PermJob {
     int64_t n = 0;
     int repeat = 0;
     int32_t* out = nullptr;                      // [repeat][n]
-    std::vector<std::vector<uint32_t>> js;       // js[r][i] = accepted j for position i (i >= 1)
+    std::vector<std::unique_ptr<uint32_t[]>> js; // js[r][i] = accepted j for position i (i >= 1); uninitialised storage
     std::vector<int> state;                      // 0 = pending, 1 = j-sequence ready, 2 = permutation ready
     std::mutex mu;
     std::condition_variable cv;
@@ -62,8 +63,8 @@ struct PermJob {
     // generator -> walker ring.  The MT19937 word stream does not depend on how many words a permutation consumes, so a
     // generator thread runs ahead (mt_gen + tempering, vectorised) while the walker does only the data-dependent part
     // (mask, compare, advance): ~0.7 ms per 524 288-element permutation instead of ~1.7 ms in one thread.
-    static constexpr int64_t kRing = 1024;       // blocks (5 KB each)
-    std::vector<MtBlock> ring;
+    static constexpr int64_t kRing = 256;        // blocks (5 KB each): the generator may run ~160 k words ahead
+    std::unique_ptr<MtBlock[]> ring;           // uninitialised storage (no 1.3 MB memset per job)
     std::atomic<int64_t> produced{0}, consumed{0};
     std::atomic<bool> stop{false};
 
@@ -98,12 +99,11 @@ struct PermJob {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return r - applied < kAhead; });
             }
-            std::vector<uint32_t>& j = js[r];
-            j.resize((size_t)(n > 0 ? n : 1));
+            js[r].reset(new uint32_t[(size_t)(n > 0 ? n : 1)]);
             // One iteration per DRAW (not per position): write the candidate, step to the next position only when it
             // is accepted (v <= i).  No data-dependent branch -- random_interval's rejection loop mispredicts ~30 % of
             // the time when written as do/while.
-            uint32_t* jd = j.data();
+            uint32_t* jd = js[r].get();
             int64_t i = n - 1;
             while (i >= 1) {
                 if (p == kMtN) {
@@ -141,9 +141,15 @@ struct PermJob {
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[r] >= 1; }); }
             int32_t* o = out + (int64_t)r * n;
             for (int64_t i = 0; i < n; ++i) o[i] = (int32_t)i;
-            const std::vector<uint32_t>& j = js[r];
-            for (int64_t i = n - 1; i >= 1; --i) { const uint32_t v = j[(size_t)i]; const int32_t t = o[v]; o[v] = o[i]; o[i] = t; }
-            std::vector<uint32_t>().swap(js[r]);
+            const uint32_t* j = js[r].get();
+            // the swap partners are known in advance: prefetch them (the 4 n-byte row does not fit a core's L1, and a dependent
+            // miss per swap is what this loop would otherwise wait on)
+            constexpr int64_t kPf = 24;
+            for (int64_t i = n - 1; i >= 1; --i) {
+                if (i > kPf) __builtin_prefetch(o + j[(size_t)(i - kPf)], 1, 1);
+                const uint32_t v = j[(size_t)i]; const int32_t t = o[v]; o[v] = o[i]; o[i] = t;
+            }
+            js[r].reset();
             { std::lock_guard<std::mutex> lk(mu); state[r] = 2; ++applied; }
             cv.notify_all();
         }
@@ -162,7 +168,7 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
         job->pos = pos; job->n = n; job->repeat = repeat; job->out = out;
         job->js.resize((size_t)repeat);
         job->state.assign((size_t)repeat, 0);
-        job->ring.resize((size_t)PermJob::kRing);
+        job->ring.reset(new MtBlock[(size_t)PermJob::kRing]);
         const int nw = n_workers < 1 ? 1 : (n_workers > repeat ? repeat : n_workers);
         job->generator = std::thread([job] { job->generate(); });
         job->producer = std::thread([job] { job->produce(); });
