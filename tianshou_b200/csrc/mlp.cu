@@ -618,8 +618,12 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_grad_kernel(
 
 // ---- clip_grad_norm_ + Adam + stats + zero_grad : one CTA ------------------------------------
 // Grid barrier / reduction state of clip_adam_kernel (self-resetting; launches are stream-ordered).
-__device__ unsigned int g_adam_arrive = 0, g_adam_depart = 0;
-__device__ double g_adam_ss = 0.0;
+// One state block per launch SLOT (the caller's stream hashed into kAdamSlots): two models updating on different streams do
+// not share barrier state, and every launch starts from a block the host zeroed on that stream (a trapped / aborted launch
+// cannot poison the next one).  The launch is cooperative: every CTA of the (<= #SMs) grid is resident, so the spin is safe.
+struct AdamCtl { unsigned int arrive, depart; double ss; };
+constexpr int kAdamSlots = 64;
+__device__ AdamCtl g_adam_ctl[kAdamSlots];
 
 // gradient fold + clip_grad_norm_ + Adam in one launch.  CTA = 256 parameters x 4 partial groups
 // (1024 threads), ~44 co-resident CTAs: (0) thread (e, q) folds the partial rows p = q (mod 4) of
@@ -630,7 +634,8 @@ constexpr int kAdamElems = 256, kAdamGroups = 4;
 __global__ void __launch_bounds__(kAdamElems * kAdamGroups) clip_adam_kernel(
     float* __restrict__ params, float* __restrict__ grad, const float* __restrict__ partials, int n_partials,
     float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int64_t* __restrict__ step_count,
-    int64_t n_params, const ts_ppo_hparams hp, float* __restrict__ stats_row) {
+    int64_t n_params, const ts_ppo_hparams hp, float* __restrict__ stats_row, int ctl_slot) {
+    AdamCtl& ctl = g_adam_ctl[ctl_slot];
     __shared__ double s_red[8];
     __shared__ float s_part[kAdamGroups][kAdamElems];
     __shared__ float s_coef, s_norm, s_step_size, s_bc2_sqrt;
@@ -668,12 +673,12 @@ __global__ void __launch_bounds__(kAdamElems * kAdamGroups) clip_adam_kernel(
     if (tid == 0) {
         double t = 0.0;
         for (int w = 0; w < kAdamElems / 32; ++w) t += s_red[w];
-        atomicAdd(&g_adam_ss, t);
+        atomicAdd(&ctl.ss, t);
         __threadfence();
-        atomicAdd(&g_adam_arrive, 1u);
-        while (*((volatile unsigned int*)&g_adam_arrive) < gridDim.x) {}
+        atomicAdd(&ctl.arrive, 1u);
+        while (*((volatile unsigned int*)&ctl.arrive) < gridDim.x) {}
         __threadfence();
-        const float total_norm = (float)sqrt(*((volatile double*)&g_adam_ss));
+        const float total_norm = (float)sqrt(*((volatile double*)&ctl.ss));
         float coef = 1.0f;
         if (hp.max_grad_norm > 0.0) {   // torch.nn.utils.clip_grad_norm_
             coef = (float)hp.max_grad_norm / (total_norm + 1e-6f);
@@ -713,10 +718,7 @@ __global__ void __launch_bounds__(kAdamElems * kAdamGroups) clip_adam_kernel(
             }
             *step_count = step;
         }
-        if (atomicAdd(&g_adam_depart, 1u) == gridDim.x - 1) {
-            g_adam_arrive = 0; g_adam_depart = 0; g_adam_ss = 0.0;
-            __threadfence();
-        }
+        (void)ctl.depart;      // the block is zeroed by the host (cudaMemsetAsync on the launch stream) before every launch
     }
 }
 
@@ -1001,7 +1003,16 @@ extern "C" int ts_clip_adam_step(float* params, float* grad, const float* partia
     TS_REQUIRE(params && grad && exp_avg && exp_avg_sq && step_count && desc && hp, "ts_clip_adam_step: null pointer");
     const unsigned adam_ctas = (unsigned)((desc->n_params + TS_PPO_GRAD_EXTRA + kAdamElems - 1) / kAdamElems);
     TS_REQUIRE(adam_ctas <= (unsigned)tsb::num_sms(), "ts_clip_adam_step: parameter vector too large for the single-wave grid barrier");
-    clip_adam_kernel<<<adam_ctas, kAdamElems * kAdamGroups, 0, tsb::as_stream(stream)>>>(params, grad, partials, n_partials, exp_avg, exp_avg_sq, step_count, desc->n_params, *hp, stats_row);
+    cudaStream_t st = tsb::as_stream(stream);
+    const int slot = (int)((reinterpret_cast<uintptr_t>(st) >> 4) % (uintptr_t)kAdamSlots);
+    void* ctl_ptr = nullptr;
+    TS_CUDA(cudaGetSymbolAddress(&ctl_ptr, g_adam_ctl));
+    TS_CUDA(cudaMemsetAsync(static_cast<AdamCtl*>(ctl_ptr) + slot, 0, sizeof(AdamCtl), st));
+    int64_t n_params = desc->n_params;
+    ts_ppo_hparams hpv = *hp;
+    int slot_arg = slot;
+    void* args[] = {&params, &grad, &partials, &n_partials, &exp_avg, &exp_avg_sq, &step_count, &n_params, &hpv, &stats_row, &slot_arg};
+    TS_CUDA(cudaLaunchCooperativeKernel((const void*)clip_adam_kernel, dim3(adam_ctas), dim3(kAdamElems * kAdamGroups), args, 0, st));
     return tsb::check_launch("ts_clip_adam_step");
 }
 

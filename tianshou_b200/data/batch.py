@@ -786,4 +786,15 @@ class NumpyGlobalPermutationJob:
             pos = C.c_int32(0)
             call("ts_host_perm_job_finish", self._job, self._key.ctypes.data_as(C.c_void_p), C.byref(pos))
             self._job = None
+            cur = np.random.get_state()
+            if cur[2] != self._st[2] or not np.array_equal(cur[1], self._st[1]):
+                # somebody drew from numpy's GLOBAL stream while the update was running (an lr-scheduler lambda, user
+                # callbacks, another thread): the `repeat` permutations were taken from the state at the START of update(), as
+                # the reference would have taken them had that draw come later.  Writing the advanced state back would replay /
+                # drop that draw, so the foreign stream position wins and the divergence is reported.
+                import warnings
+                warnings.warn("numpy's global RNG was used while Algorithm.update() was drawing its minibatch permutations; "
+                              "the global stream is left as that draw put it (it no longer matches the reference's)", RuntimeWarning,
+                              stacklevel=2)
+                return
             np.random.set_state((self._st[0], self._key, pos.value, self._st[3], self._st[4]))
