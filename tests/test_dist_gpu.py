@@ -20,7 +20,7 @@ def _free_port() -> int:
     return p
 
 
-def _worker(rank: int, world_size: int, port: int, variant: str, path: str, out_dir: str) -> None:
+def _worker(rank: int, world_size: int, port: int, variant: str, path: str, out_dir: str, partition: str = "per_rank") -> None:
     import torch.distributed as dist
 
     from test_ppo_gpu import ppo_kwargs
@@ -36,7 +36,8 @@ def _worker(rank: int, world_size: int, port: int, variant: str, path: str, out_
         g = load_golden(f"ppo_ref_{variant}.npz")
         kw = ppo_kwargs(g)
         lr = float(g["kw_lr"]) if "kw_lr" in g.files else 3e-4
-        algo, actor, critic = build_ppo(17, 6, dev, lr=lr, params={k: g["p0_" + k] for k in PARAM_ORDER}, **kw)
+        algo, actor, critic = build_ppo(17, 6, dev, lr=lr, params={k: g["p0_" + k] for k in PARAM_ORDER},
+                                        rollout_partition=partition, **kw)
         bs = int(g["cfg_bs"])
         for u in range(2):
             buf = restore_vector_buffer(g, f"u{u}_", int(g["cfg_E"]), int(g["cfg_cap"]), device=dev)
@@ -52,8 +53,12 @@ def _worker(rank: int, world_size: int, port: int, variant: str, path: str, out_
             for k, pv in named_params(actor, critic).items():
                 np.testing.assert_allclose(pv.detach().cpu().numpy(), g[f"u{u}_p_" + k], rtol=2e-3, atol=3e-5,
                                            err_msg=f"rank {rank} update {u} {k}")
-            if kw["return_scaling"]:   # two identical shards: same mean / var, twice the count
+            if kw["return_scaling"]:   # two identical shards: same mean / var, twice the count (shared rollout: the count too)
                 np.testing.assert_allclose([algo.ret_rms.mean, algo.ret_rms.var], g[f"u{u}_rms"][:2], rtol=1e-5)
+                if partition == "shared":
+                    np.testing.assert_allclose(algo.ret_rms.count, g[f"u{u}_rms"][2], rtol=1e-12)
+            if partition == "shared":  # the SAME problem as the reference run: the per-minibatch loss table must match row by row
+                np.testing.assert_allclose(algo.last_loss_table[:, :4], ref_losses, rtol=2e-4, atol=2e-5)
         torch.save(algo._flat.flat.cpu(), os.path.join(out_dir, f"flat{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -68,3 +73,15 @@ def test_two_rank_update_matches_reference(variant, path, tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), variant, path, str(tmp_path)), nprocs=2, join=True)
     a, b = torch.load(tmp_path / "flat0.pt"), torch.load(tmp_path / "flat1.pt")
     assert torch.equal(a, b), "replicas diverged"      # same all-reduced gradient, same Adam step: bit-identical
+
+
+@pytest.mark.parametrize("variant", ["A", "B"])
+def test_two_rank_shared_rollout_matches_reference(variant, tmp_path):
+    """Strong scaling: ONE rollout, the same ``np.random.permutation`` stream on both ranks, every minibatch split
+    into two contiguous slices, gradient sum inside the epoch kernel -> the reference run's results, loss table row by row."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), variant, "p2p", str(tmp_path), "shared"), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "flat0.pt"), torch.load(tmp_path / "flat1.pt")
+    assert torch.equal(a, b), "replicas diverged"
