@@ -577,6 +577,12 @@ def main() -> None:
             line["offpolicy"] = offpolicy_extras(dev)
         except Exception as ex:  # noqa: BLE001 - extras must never take the headline down
             line["offpolicy"] = {"error": repr(ex)}
+        try:        # context only: the reference's own style of update with stock PyTorch on the same GPU
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import torch_eager_context
+            line["context_torch_eager_gpu"] = torch_eager_context.run(E=E, T=T, bs=BS, repeat=REPEAT, steps=1, device=str(dev))
+        except Exception as ex:  # noqa: BLE001
+            line["context_torch_eager_gpu"] = {"error": repr(ex)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
