@@ -210,6 +210,18 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
         if self._layered is not None:
             self._layered.critic_values(batch.obs, v_s)
             self._layered.critic_values(batch.obs_next, v_next)
+        elif self._shared_world() > 1 and n % self._shared_world() == 0:
+            # shared rollout on several GPUs: every rank evaluates the critic on ITS 1 / world of the rows (contiguous env range),
+            # one all-gather makes v_s / v_s_ complete everywhere; the 17 us scan below runs redundantly (replicas identical)
+            import torch.distributed as dist
+            w, r = self._shared_world(), dist.get_rank()
+            lo, hi = r * (n // w), (r + 1) * (n // w)
+            pair = self._buf("v_pair_local", (2, n // w), torch.float32)
+            ops.critic_forward(self._flat.flat, self._desc, batch.obs[lo:hi], batch.obs_next[lo:hi], out=pair[0], out2=pair[1])
+            full = self._buf("v_pair_full", (w, 2, n // w), torch.float32)
+            dist.all_gather_into_tensor(full, pair)
+            v_s.view(w, n // w).copy_(full[:, 0])
+            v_next.view(w, n // w).copy_(full[:, 1])
         else:
             ops.critic_forward(self._flat.flat, self._desc, batch.obs, batch.obs_next, out=v_s, out2=v_next)
         rms = self._rms_device() if self.return_scaling else None
@@ -250,6 +262,12 @@ class ActorCriticOnPolicyAlgorithm(OnPolicyAlgorithm, ABC):
             self.ret_rms.load_device_state(self._scratch.pop("rms"))
 
     # ------------------------------------------------------------------ multi-GPU hooks
+    def _shared_world(self) -> int:
+        """World size if this algorithm runs data-parallel on ONE shared rollout (rollout_partition='shared'), else 1."""
+        if getattr(self, "data_parallel", True) and getattr(self, "rollout_partition", "per_rank") == "shared":
+            return self._world_size()
+        return 1
+
     @staticmethod
     def _world_size() -> int:
         import torch.distributed as dist

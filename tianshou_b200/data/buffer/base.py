@@ -221,11 +221,21 @@ class ReplayBuffer:
     def device_meta(self) -> ops.DeviceBufferMeta:
         """(edges, done, last_index, lengths) on the device, refreshed when the buffer changed."""
         if self._mirror is None or self._mirror_version != self._version:
-            done = self._meta.get("done")
-            if done is None or (isinstance(done, Batch)):
-                done = np.zeros(self.maxsize, dtype=bool)
-            self.__dict__["_mirror"] = ops.DeviceBufferMeta.from_host(
-                self._extend_offset, done, self.last_index, self._sizes, self.device, ins=self._ins)
+            cols = self.device_columns()
+            if cols is not None and "done" in cols:
+                # the B-sized `done` column is already on the device (mirror, kept current by add()): only the E-sized
+                # bookkeeping arrays travel -- an off-policy loop (collect a step, update, ...) refreshes this every update
+                dev = self.device
+                self.__dict__["_mirror"] = ops.DeviceBufferMeta(
+                    to_device(np.asarray(self._extend_offset, dtype=np.int64), dev), cols["done"].view(torch.uint8),
+                    to_device(np.asarray(self.last_index, dtype=np.int64), dev), to_device(np.asarray(self._sizes, dtype=np.int64), dev),
+                    to_device(np.asarray(self._ins, dtype=np.int64), dev))
+            else:
+                done = self._meta.get("done")
+                if done is None or (isinstance(done, Batch)):
+                    done = np.zeros(self.maxsize, dtype=bool)
+                self.__dict__["_mirror"] = ops.DeviceBufferMeta.from_host(
+                    self._extend_offset, done, self.last_index, self._sizes, self.device, ins=self._ins)
             self.__dict__["_mirror_version"] = self._version
         return self._mirror
 
