@@ -610,6 +610,9 @@ def offpolicy_extras(dev) -> dict:
 
     out: dict = {}
     rng = np.random.default_rng(0)
+    # batch-256 MLPs / batch-32 convolutions do not scale past a few cores: give the CPU port its best case, not every core
+    cpu_threads = min(8, os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads)
 
     def time_updates(fn, warm: int, iters: int) -> float:
         for _ in range(warm):

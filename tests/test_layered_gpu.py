@@ -46,8 +46,9 @@ def _run_updates(algo, g, tag, params_fn, lr):
         ref_losses = g[o + "losses"]
         assert stats.gradient_steps == ref_losses.shape[0]
         for col, name in enumerate(["loss", "actor_loss", "vf_loss", "ent_loss"]):
+            # (absolute floor 5e-7: a surrogate loss that averages to ~1e-3 is a mean of O(1) terms)
             record_parity(f"{tag}_u{u}/per_step_{name}", algo.last_loss_table[:, col], ref_losses[:, col], rtol=2e-4,
-                          atol=2e-5 * max(1e-3, float(np.abs(ref_losses[:, col]).max())))
+                          atol=5e-7 + 2e-5 * max(1e-3, float(np.abs(ref_losses[:, col]).max())))
         for k, pv in params_fn().items():
             record_parity(f"{tag}_u{u}/param_{k}", pv.detach().cpu().numpy(), g[o + "p_" + k], rtol=1e-3, atol=0.1 * lr)
 

@@ -52,7 +52,8 @@ struct PermJob {
     int repeat = 0;
     int32_t* out = nullptr;                      // [repeat][n]
     std::vector<std::unique_ptr<uint32_t[]>> js; // js[r][i] = accepted j for position i (i >= 1); uninitialised storage
-    std::vector<int> state;                      // 0 = pending, 1 = j-sequence ready, 2 = permutation ready
+    std::vector<int> state;                      // 0 = pending, 1 = walk started (j storage exists), 2 = permutation ready
+    std::unique_ptr<std::atomic<int64_t>[]> progress;   // per pass: every position ABOVE this one has its final j (streamed to the applier)
     std::mutex mu;
     std::condition_variable cv;
     std::thread generator, producer;
@@ -100,14 +101,18 @@ struct PermJob {
                 cv.wait(lk, [&] { return r - applied < kAhead; });
             }
             js[r].reset(new uint32_t[(size_t)(n > 0 ? n : 1)]);
+            progress[r].store(n - 1, std::memory_order_relaxed);
+            { std::lock_guard<std::mutex> lk(mu); state[r] = 1; }     // the applier may start: it follows `progress`
+            cv.notify_all();
             // One iteration per DRAW (not per position): write the candidate, step to the next position only when it
             // is accepted (v <= i).  No data-dependent branch -- random_interval's rejection loop mispredicts ~30 % of
-            // the time when written as do/while.
+            // the time when written as do/while.  Four draws per bounds check: i drops by at most one per draw.
             uint32_t* jd = js[r].get();
             int64_t i = n - 1;
             while (i >= 1) {
                 if (p == kMtN) {
                     consumed.store(b + 1, std::memory_order_release);
+                    progress[r].store(i, std::memory_order_release);
                     ++b; p = 0;
                     blk = &block(b);
                 }
@@ -118,6 +123,12 @@ struct PermJob {
                     // positions i in (lower, mask] share one mask: the loop-carried chain is just compare + subtract
                     const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
                     const int64_t lower = (int64_t)(mask >> 1);
+                    for (; d + 4 <= avail && i - 4 > lower; d += 4) {
+                        const uint32_t v0 = tmp[d] & mask;     jd[i] = v0; i -= (int64_t)(v0 <= (uint32_t)i);
+                        const uint32_t v1 = tmp[d + 1] & mask; jd[i] = v1; i -= (int64_t)(v1 <= (uint32_t)i);
+                        const uint32_t v2 = tmp[d + 2] & mask; jd[i] = v2; i -= (int64_t)(v2 <= (uint32_t)i);
+                        const uint32_t v3 = tmp[d + 3] & mask; jd[i] = v3; i -= (int64_t)(v3 <= (uint32_t)i);
+                    }
                     for (; d < avail && i > lower; ++d) {
                         const uint32_t v = tmp[d] & mask;
                         jd[i] = v;
@@ -126,8 +137,7 @@ struct PermJob {
                 }
                 p += d;
             }
-            { std::lock_guard<std::mutex> lk(mu); state[r] = 1; }
-            cv.notify_all();
+            progress[r].store(0, std::memory_order_release);
         }
         // final generator state = numpy's (key, pos) after these draws: the current block's key, next unconsumed word
         std::memcpy(key, blk->key, sizeof(key));
@@ -142,11 +152,17 @@ struct PermJob {
             int32_t* o = out + (int64_t)r * n;
             for (int64_t i = 0; i < n; ++i) o[i] = (int32_t)i;
             const uint32_t* j = js[r].get();
-            // the swap partners are known in advance: prefetch them (the 4 n-byte row does not fit a core's L1, and a dependent
-            // miss per swap is what this loop would otherwise wait on)
+            // The swaps follow the walker as it goes (positions above progress[r] are final): the first pass of an update is
+            // ready ~max(walk, apply) after the start instead of walk + apply.  The swap partners are known in advance:
+            // prefetch them (the 4 n-byte row does not fit a core's L1; a dependent miss per swap is what this loop would wait on).
             constexpr int64_t kPf = 24;
+            int64_t safe = progress[r].load(std::memory_order_acquire);       // positions > safe may be applied
             for (int64_t i = n - 1; i >= 1; --i) {
-                if (i > kPf) __builtin_prefetch(o + j[(size_t)(i - kPf)], 1, 1);
+                while (i <= safe && safe > 0) {
+                    std::this_thread::yield();
+                    safe = progress[r].load(std::memory_order_acquire);
+                }
+                if (i - kPf > safe) __builtin_prefetch(o + j[(size_t)(i - kPf)], 1, 1);
                 const uint32_t v = j[(size_t)i]; const int32_t t = o[v]; o[v] = o[i]; o[i] = t;
             }
             js[r].reset();
@@ -168,6 +184,8 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
         job->pos = pos; job->n = n; job->repeat = repeat; job->out = out;
         job->js.resize((size_t)repeat);
         job->state.assign((size_t)repeat, 0);
+        job->progress.reset(new std::atomic<int64_t>[(size_t)repeat]);
+        for (int r = 0; r < repeat; ++r) job->progress[r].store(n, std::memory_order_relaxed);
         job->ring.reset(new MtBlock[(size_t)PermJob::kRing]);
         const int nw = n_workers < 1 ? 1 : (n_workers > repeat ? repeat : n_workers);
         job->generator = std::thread([job] { job->generate(); });
