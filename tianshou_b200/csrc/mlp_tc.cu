@@ -926,6 +926,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
         gbar.wait();                                                // every partial row is complete
         tstamp(11);
         if (pre) { store_inputs(pin); staged = true; }
+        tstamp(23);
         // fold: thread (e, q) sums rows q, q + 4, ... of element i0 + e [+ 128, ...]; 32 loads in flight
         double ss = 0.0;
         for (int64_t c = i0; c < i1; c += 128) {
@@ -945,6 +946,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             }
             s_part[q][e] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
             __syncthreads();
+            tstamp(24);
             if (q == 0 && i < i1) {
                 float g = (s_part[0][e] + s_part[1][e]) + (s_part[2][e] + s_part[3][e]);
                 if (px.world > 1) {
@@ -994,6 +996,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             if (blockIdx.x == 0) ctl->ss[(m + 1) & 1] = 0.0;       // next step's accumulator (idle until barrier 3)
         }
         __syncthreads();
+        tstamp(25);
         const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
         const float w1 = (float)(1.0 - hp.beta1), w2 = (float)(1.0 - hp.beta2);
         const float beta2 = (float)hp.beta2, adam_eps = (float)hp.adam_eps, wd = (float)hp.weight_decay;
@@ -1013,6 +1016,7 @@ __global__ void __launch_bounds__(kThreads, 1) ppo_tc_kernel(
             for (int64_t i = i0 + tid; i < i1 && i < d.n_params; i += kThreads)
                 adam_elem(i, opt.grad_scratch[i], opt.params_w[i], opt.exp_avg[i], opt.exp_avg_sq[i]);
         }
+        tstamp(26);
         if (wimg != nullptr) umma::fence_proxy_async_all();      // image stores (generic proxy) before the peers' bulk copies
         tstamp(14);
         const bool more = m + 1 < n_mb;
