@@ -195,6 +195,7 @@ class FusedStack:
         self.name = name
         self.device = group.device
         self._bufs: dict[tuple, torch.Tensor] = {}
+        self._ws_sizes: dict[tuple[int, int, int], int] = {}
         self._lib = load_library()
 
     # ------------------------------------------------------------------ scratch
@@ -206,7 +207,9 @@ class FusedStack:
 
     def _gemm(self, a, lda, a_mn, b, ldb, b_mn, c, ldc, M, N, K, bias=None, act=ACT_NONE, mask=None, ld_mask=0,
               mask_kind=ACT_RELU, accumulate=False) -> None:
-        ws_n = int(self._lib.ts_net_gemm_workspace_floats(M, N, K))
+        ws_n = self._ws_sizes.get((M, N, K))
+        if ws_n is None:
+            ws_n = self._ws_sizes[(M, N, K)] = int(self._lib.ts_net_gemm_workspace_floats(M, N, K))
         ws = self._buf(("ws",), ws_n) if ws_n > 0 else None
         call("ts_net_gemm", a, lda, a_mn, b, ldb, b_mn, c, ldc, M, N, K, bias, act, mask, ld_mask, int(mask_kind), int(accumulate),
              ptr(ws) if ws is not None else None, ws_n, stream_ptr(self.device))
