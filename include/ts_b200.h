@@ -472,6 +472,11 @@ int ts_mean(const float* x, int64_t n, float* out, ts_stream_t stream);
 int ts_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step, double lr,
                  double beta1, double beta2, double eps, double weight_decay, double max_grad_norm, double* norm_scratch,
                  ts_stream_t stream);
+/* the same step with the step counter in DEVICE memory (*step_dev = steps taken so far; incremented by the call): no host-side
+ * state in the launch, so a captured CUDA graph containing it can be replayed update after update */
+int ts_adam_step_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, double max_grad_norm, double* norm_scratch,
+                     ts_stream_t stream);
 /* target = tau * source + (1 - tau) * target   (utils/lagged_network.py:8-18) */
 int ts_polyak_update(float* target, const float* source, int64_t n, double tau, ts_stream_t stream);
 

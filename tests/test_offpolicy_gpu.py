@@ -39,7 +39,7 @@ def _check_params(tag, mod, g, prefix, lr):
 
 
 # ------------------------------------------------------------------------------------------------------------ SAC
-def _build_sac(g):
+def _build_sac(g, **kw):
     from tianshou_b200.algorithm import AdamOptimizerFactory
     from tianshou_b200.algorithm.modelfree.sac import SAC, SACPolicy
     from tianshou_b200.utils.net.common import Net
@@ -54,7 +54,7 @@ def _build_sac(g):
     policy = SACPolicy(actor=actor, action_space=_Box(A))
     algo = SAC(policy=policy, policy_optim=AdamOptimizerFactory(lr=lr), critic=c1, critic_optim=AdamOptimizerFactory(lr=lr),
                critic2=c2, critic2_optim=AdamOptimizerFactory(lr=lr), tau=float(g["cfg_tau"]), gamma=float(g["cfg_gamma"]),
-               alpha=float(g["cfg_alpha"]), n_step_return_horizon=int(g["cfg_n_step"]))
+               alpha=float(g["cfg_alpha"]), n_step_return_horizon=int(g["cfg_n_step"]), **kw)
     return algo, actor, c1, c2, lr
 
 
@@ -95,6 +95,37 @@ def test_sac_update_matches_reference(mirror):
         _check_params(tag, actor, g, o + "actor_", lr); _check_params(tag, c1, g, o + "c1_", lr); _check_params(tag, c2, g, o + "c2_", lr)
         _check_params(tag, algo.critic_old, g, o + "c1old_", lr); _check_params(tag, algo.critic2_old, g, o + "c2old_", lr)
         assert stats.alpha == pytest.approx(float(g["cfg_alpha"])) and stats.alpha_loss is None and stats.train_time > 0
+
+
+def test_sac_cuda_graph_matches_reference():
+    """``SAC(cuda_graph=True)``: update 0 runs eagerly, update 1 is captured and replayed, later updates are replays of the same
+    graph — every one of them must still match the reference's update on the same indices / noise."""
+    from tianshou_b200.data import Batch, VectorReplayBuffer
+    from tianshou_b200.utils import policy_within_training_step
+    g = load_golden("sac_ref.npz")
+    algo, actor, c1, c2, lr = _build_sac(g, cuda_graph=True)
+    E, cap = int(g["cfg_E"]), int(g["cfg_cap"])
+    buf = VectorReplayBuffer(E * cap, E, device=DEV, device_mirror=True)
+    buf.set_batch(Batch(**{k: g["buf_" + k].copy() for k in ("obs", "act", "rew", "terminated", "truncated", "done", "obs_next")}))
+    set_buffer_state(buf, g["meta_last_index"], g["meta_lengths"])
+    buf.sync_device_mirror()
+    algo._noise_fn = lambda shape: torch.normal(torch.zeros(shape), torch.ones(shape)).to(DEV)
+    n_up = int(g["cfg_updates"])
+    assert n_up >= 3, "need an eager, a capture and a pure-replay update"
+    for u in range(n_up):
+        torch.manual_seed(100 + u)
+        with policy_within_training_step(algo.policy):
+            stats = algo.update(buffer=buf, sample_size=int(g["cfg_bs"]))
+        o, tag = f"u{u}_", f"sac_graph_u{u}"
+        assert np.array_equal(algo._graph["h_idx"].numpy(), g[o + "indices"]), "sampled indices differ from the reference's"
+        got = np.array([stats.actor_loss, stats.critic1_loss, stats.critic2_loss])
+        record_parity(f"{tag}/losses", got, g[o + "losses"], rtol=2e-5, atol=2e-6)
+        _check_params(tag, actor, g, o + "actor_", lr); _check_params(tag, c1, g, o + "c1_", lr); _check_params(tag, c2, g, o + "c2_", lr)
+        _check_params(tag, algo.critic_old, g, o + "c1old_", lr); _check_params(tag, algo.critic2_old, g, o + "c2old_", lr)
+    assert algo._graph["graph"] is not None and algo._graph["calls"] == n_up
+    for grp in algo._g_c:
+        grp.sync_step_from_device()
+        assert grp.step == n_up
 
 
 def test_sac_policy_forward_collector_path():

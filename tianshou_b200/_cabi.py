@@ -121,6 +121,7 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_sac_actor_q_grad": [_P, _P, _P, C.c_float, _I64, _P, _P, _P, _P],
     "ts_mean": [_P, _I64, _P, _P],
     "ts_adam_step": [_P, _P, _P, _P, _I64, _I64, _D, _D, _D, _D, _D, _D, _P, _P],
+    "ts_adam_step_dev": [_P, _P, _P, _P, _I64, _P, _D, _D, _D, _D, _D, _D, _P, _P],
     "ts_polyak_update": [_P, _P, _I64, _D, _P],
 }
 # diagnostics build only (libts_b200_diag.so, tools/): not part of the product library

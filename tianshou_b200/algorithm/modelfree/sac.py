@@ -186,7 +186,7 @@ class SAC(OffPolicyAlgorithm):
     def __init__(self, *, policy: SACPolicy, policy_optim: OptimizerFactory, critic: nn.Module, critic_optim: OptimizerFactory,
                  critic2: nn.Module | None = None, critic2_optim: OptimizerFactory | None = None, tau: float = 0.005,
                  gamma: float = 0.99, alpha: float | Alpha = 0.2, n_step_return_horizon: int = 1,
-                 deterministic_eval: bool = True) -> None:
+                 deterministic_eval: bool = True, cuda_graph: bool = False) -> None:
         assert 0.0 <= tau <= 1.0, f"tau should be in [0, 1] but got: {tau}"
         assert 0.0 <= gamma <= 1.0, f"gamma should be in [0, 1] but got: {gamma}"
         super().__init__(policy=policy)
@@ -226,6 +226,11 @@ class SAC(OffPolicyAlgorithm):
                 raise UnsupportedModelError("optimizer parameters differ from the fused network's parameters")
             o._flat = g
         self._scratch: dict[str, torch.Tensor] = {}
+        # opt-in: the device work of one update() (~85 launches) captured once into a CUDA graph and replayed -- the eager call
+        # sequence is Python-launch bound.  Needs a buffer with a device mirror, uniform replay and a fixed alpha.
+        self.cuda_graph = bool(cuda_graph)
+        self._graph: dict[str, Any] = {}
+        self._adam = FlatGroup.adam_step          # the graphed body switches to the device-step variant
         # rsample noise source: torch's generator on the networks' device (what the reference draws when it runs there)
         self._noise_fn = lambda shape: torch.normal(torch.zeros(shape, device=dev), torch.ones(shape, device=dev))
 
@@ -240,7 +245,8 @@ class SAC(OffPolicyAlgorithm):
     def _rows(self, buffer: ReplayBuffer, key: str, indices: np.ndarray | torch.Tensor) -> torch.Tensor:
         """buffer[key][indices] as a dense fp32 [I, width] device tensor: gathered from the device mirror when the
         buffer keeps one (no host traffic), else a host gather of the sampled rows + one upload."""
-        cols = buffer.device_columns() if hasattr(buffer, "device_columns") else None
+        cols = self._cols_override if self._cols_override is not None else (
+            buffer.device_columns() if hasattr(buffer, "device_columns") else None)
         if cols is not None and key in cols:
             from ... import ops
             idx = indices if isinstance(indices, torch.Tensor) else to_device(np.asarray(indices, dtype=np.int64), self._dev)
@@ -315,7 +321,7 @@ class SAC(OffPolicyAlgorithm):
         call("ts_critic_mse", ptr(q), ptr(returns), ptr(weight), B, ptr(td), ptr(dq), ptr(rows), st)
         call("ts_mean", ptr(rows), B, ptr(out_loss), st)
         self._c[k].backward(acts, dq, B, "cu")
-        self._g_c[k].adam_step(optim._optim, optim._max_grad_norm)
+        self._adam(self._g_c[k], optim._optim, optim._max_grad_norm)
         return td
 
     def _update_with_batch(self, batch: Batch) -> SACTrainingStats:
@@ -349,14 +355,106 @@ class SAC(OffPolicyAlgorithm):
         call("ts_squashed_gaussian_bwd", ptr(a_acts[-1]), 2 * A, ptr(noise), ptr(new_act), ptr(sigma), ptr(dact), B, A,
              SIGMA_MIN, SIGMA_MAX, _F32_EPS, alpha / B, ptr(dhead), st)
         self._actor.backward(a_acts, dhead, B, "au")
-        self._g_actor.adam_step(self.policy_optim._optim, self.policy_optim._max_grad_norm)
+        self._adam(self._g_actor, self.policy_optim._optim, self.policy_optim._max_grad_norm)
 
-        alpha_loss = self.alpha.update(-logp.detach().unsqueeze(-1))
+        alpha_loss = None if self._in_graph_body else self.alpha.update(-logp.detach().unsqueeze(-1))
         for k in range(2):                      # _update_lagged_network_weights
             polyak_update(self._g_ct[k], self._g_c[k], self.tau)
+        if self._in_graph_body:
+            return None                         # the losses stay on the device; update() reads them after the replay
         l = losses.cpu().numpy()                # the only host sync of the update
         return SACTrainingStats(actor_loss=float(l[2]), critic1_loss=float(l[0]), critic2_loss=float(l[1]),
                                 alpha=float(self.alpha.value), alpha_loss=alpha_loss)
+
+    # ------------------------------------------------------------------ CUDA-graph mode
+    _in_graph_body = False
+    _cols_override: Any = None          # the mirror's columns while the graphed body runs (no cross-stream wait inside a capture)
+
+    def _graph_usable(self, buffer: ReplayBuffer) -> bool:
+        cols = buffer.device_columns() if hasattr(buffer, "device_columns") else None
+        return (self.cuda_graph and isinstance(self.alpha, FixedAlpha) and not hasattr(buffer, "update_weight") and cols is not None
+                and buffer._save_obs_next and all(k in cols for k in ("obs", "act", "rew", "terminated", "done", "obs_next")))
+
+    def _device_body(self, buffer: ReplayBuffer, g: dict[str, Any]) -> None:
+        """Everything of one update() after the index / noise draws, with no host synchronisation: n-step chain, target,
+        both critic steps, the actor step, Polyak.  Runs eagerly once, then inside the capture, then as graph replays."""
+        from ... import ops
+        idx, meta, cols = g["idx"], g["meta"], g["cols"]
+        noise_iter = iter((g["noise"][0], g["noise"][1]))
+        saved_fn, self._noise_fn = self._noise_fn, lambda shape: next(noise_iter)
+        saved_adam, self._adam = self._adam, FlatGroup.adam_step_device
+        self._in_graph_body, self._cols_override = True, cols
+        try:
+            B = idx.numel()
+            n = self.n_step_return_horizon
+            stacked = ops.stack_next_indices(meta, idx, n)
+            last = stacked[-1].contiguous()
+            tq = self._target_q(buffer, last).reshape(B, -1).clone()
+            ops.value_mask_rows(tq, cols["terminated"].view(torch.uint8), last)
+            rew = cols["rew"] if cols["rew"].dtype == torch.float64 else cols["rew"].to(torch.float64)
+            returns = ops.nstep_return(rew, ops.buffer_end_flags(meta), tq, stacked, self.gamma, n, out_dtype=torch.float64)
+            batch = Batch()
+            batch.__dict__["obs"] = self._rows(buffer, "obs", idx).contiguous()
+            batch.__dict__["act"] = self._rows(buffer, "act", idx).contiguous()
+            batch.__dict__["returns"] = returns.to(torch.float32)
+            self._update_with_batch(batch)
+            g["h_losses"].copy_(self._buf("losses", 3), non_blocking=True)
+        finally:
+            self._noise_fn, self._adam, self._in_graph_body, self._cols_override = saved_fn, saved_adam, False, None
+
+    def update(self, buffer: ReplayBuffer, sample_size: int | None) -> TrainingStats:
+        """``OffPolicyAlgorithm.update`` (algorithm_base.py:868-903); with ``cuda_graph=True`` the device work is one graph replay."""
+        if buffer is None or not self.policy.is_within_training_step or not self._graph_usable(buffer):
+            return super().update(buffer, sample_size)
+        import time
+
+        from ...ops import DeviceBufferMeta
+        from ...utils.torch_utils import torch_train_mode
+        start = time.time()
+        dev = self._dev
+        indices = np.asarray(buffer.sample_indices(sample_size), dtype=np.int64)
+        B, A = len(indices), self.act_dim
+        cols = buffer.device_columns()                       # also orders this stream after the mirror's pending copies
+        E = int(buffer.buffer_num)
+        g = self._graph
+        key = (B, E, tuple(int(cols[k].data_ptr()) for k in sorted(cols)), float(self.policy_optim._optim.param_groups[0]["lr"]),
+               float(self.critic_optim._optim.param_groups[0]["lr"]), float(self.critic2_optim._optim.param_groups[0]["lr"]))
+        if g.get("key") != key:                              # (re)build the persistent inputs; the next call captures
+            g.clear()
+            g.update(key=key, calls=0, graph=None, cols=dict(cols),
+                     h_idx=torch.empty(B, dtype=torch.int64, pin_memory=True), idx=torch.empty(B, dtype=torch.int64, device=dev),
+                     h_meta=torch.empty((3, E), dtype=torch.int64, pin_memory=True), d_meta=torch.empty((3, E), dtype=torch.int64, device=dev),
+                     noise=torch.empty((2, B, A), dtype=torch.float32, device=dev), h_losses=torch.empty(3, dtype=torch.float32, pin_memory=True))
+            off = torch.from_numpy(np.asarray(buffer._extend_offset, dtype=np.int64)).to(dev)
+            g["meta"] = DeviceBufferMeta(off, cols["done"].view(torch.uint8), g["d_meta"][0], g["d_meta"][1], g["d_meta"][2])
+        g["h_idx"].numpy()[...] = indices
+        hm = g["h_meta"].numpy()
+        hm[0], hm[1], hm[2] = buffer.last_index, buffer._sizes, buffer._ins
+        g["idx"].copy_(g["h_idx"], non_blocking=True)
+        g["d_meta"].copy_(g["h_meta"], non_blocking=True)
+        g["noise"][0].copy_(self._noise_fn((B, A)).to(dev, torch.float32))      # the two rsample draws, in the reference's order
+        g["noise"][1].copy_(self._noise_fn((B, A)).to(dev, torch.float32))
+        with torch_train_mode(self):
+            if g["graph"] is not None:
+                g["graph"].replay()
+            elif g["calls"] == 0:                            # first update with these shapes: eager (allocates every scratch buffer)
+                self._device_body(buffer, g)
+            else:                                            # second: capture, then replay it as this update
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(dev)
+                with torch.cuda.graph(graph):
+                    self._device_body(buffer, g)
+                g["graph"] = graph
+                graph.replay()
+        g["calls"] += 1
+        torch.cuda.current_stream(dev).synchronize()         # the one host sync: the three loss scalars
+        l = g["h_losses"].numpy()
+        for sched in self.lr_schedulers:
+            sched.step()
+        stat = SACTrainingStats(actor_loss=float(l[2]), critic1_loss=float(l[0]), critic2_loss=float(l[1]), alpha=float(self.alpha.value),
+                                alpha_loss=None)
+        stat.train_time = time.time() - start
+        return stat
 
 
 def _space_name(space: Any) -> str:

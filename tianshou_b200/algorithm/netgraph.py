@@ -36,6 +36,7 @@ class FlatGroup:
         self.exp_avg_sq = torch.zeros(self.n, dtype=torch.float32, device=device)
         self.norm_scratch = torch.zeros(256, dtype=torch.float64, device=device)
         self.step = 0
+        self.step_dev: torch.Tensor | None = None     # device-resident step counter (CUDA-graph mode: see adam_step_device)
         self._offsets: dict[int, int] = {}
         off = 0
         for p in self.params:
@@ -67,12 +68,30 @@ class FlatGroup:
     def adam_step(self, optimizer: torch.optim.Optimizer, max_grad_norm: float | None) -> None:
         """``Algorithm.Optimizer.step`` after backward: clip_grad_norm_ (optional) + Adam (algorithm_base.py:496-500)."""
         hp = adam_hyperparams(optimizer)
+        self.sync_step_from_device()
         self.step += 1
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.step)
         call("ts_adam_step", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n, self.step,
              hp["lr"], hp["beta1"], hp["beta2"], hp["adam_eps"], hp["weight_decay"], float(max_grad_norm or 0.0),
              ptr(self.norm_scratch), stream_ptr(self.device))
 
+    def adam_step_device(self, optimizer: torch.optim.Optimizer, max_grad_norm: float | None) -> None:
+        """Same step with the step number read from / advanced in DEVICE memory: nothing in the launch depends on host state,
+        so it can live inside a captured CUDA graph (the host mirror ``self.step`` is re-read by ``sync_step_from_device``)."""
+        hp = adam_hyperparams(optimizer)
+        if self.step_dev is None:
+            self.step_dev = torch.tensor([self.step], dtype=torch.int64, device=self.device)
+        call("ts_adam_step_dev", ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.n, ptr(self.step_dev),
+             hp["lr"], hp["beta1"], hp["beta2"], hp["adam_eps"], hp["weight_decay"], float(max_grad_norm or 0.0),
+             ptr(self.norm_scratch), stream_ptr(self.device))
+
+    def sync_step_from_device(self) -> None:
+        if self.step_dev is not None:
+            self.step = int(self.step_dev.item())
+
     def export_state(self, optimizer: torch.optim.Optimizer) -> None:
+        self.sync_step_from_device()
         if self.step == 0 and len(optimizer.state) == 0:
             return
         for p in self.params:
@@ -95,6 +114,8 @@ class FlatGroup:
         if steps and max(steps) != min(steps):
             raise UnsupportedModelError("per-parameter Adam step counts differ; cannot fuse")
         self.step = int(round(steps[0])) if steps else 0
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.step)
 
 
 def polyak_update(target: FlatGroup, source: FlatGroup, tau: float) -> None:

@@ -299,6 +299,41 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         m[i] = mm; v[i] = vv; p[i] = pv;
     }
 }
+// Same step with the 1-based step number read from DEVICE memory (*step_dev + 1): the launch carries no host-side state, so a
+// CUDA graph that contains it stays valid from one replay to the next.  step_inc_kernel advances the counter afterwards.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                const int64_t* __restrict__ step_dev, double lr, double beta1d, double beta2d, float eps, float wd,
+                                float max_norm, const double* __restrict__ partial, int n_partial) {
+    __shared__ float s_step_size, s_bc2_sqrt, s_coef;
+    if (threadIdx.x == 0) {
+        const double step = (double)(*step_dev + 1);
+        s_step_size = (float)(lr / (1.0 - pow(beta1d, step)));
+        s_bc2_sqrt = (float)sqrt(1.0 - pow(beta2d, step));
+        float coef = 1.0f;
+        if (max_norm > 0.0f && partial) {
+            double t = 0.0;
+            for (int i = 0; i < n_partial; ++i) t += partial[i];
+            coef = fminf(max_norm / ((float)sqrt(t) + 1e-6f), 1.0f);
+        }
+        s_coef = coef;
+    }
+    __syncthreads();
+    const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt, coef = s_coef;
+    const float beta1 = (float)beta1d, beta2 = (float)beta2d;
+    const float w1 = 1.0f - beta1, w2 = 1.0f - beta2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * coef;
+        float pv = p[i];
+        if (wd != 0.0f) gi = fmaf(wd, pv, gi);
+        float mm = m[i], vv = v[i];
+        mm = mm + w1 * (gi - mm);
+        vv = vv * beta2 + w2 * gi * gi;
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;
+        pv = pv - step_size * (mm / denom);
+        m[i] = mm; v[i] = vv; p[i] = pv;
+    }
+}
+__global__ void step_inc_kernel(int64_t* step_dev) { *step_dev += 1; }
 // tgt = tau * src + (1 - tau) * tgt, each product rounded to fp32 before the add (torch evaluates two muls and an add)
 __global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, int64_t n, float tau, float one_minus_tau) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -407,6 +442,25 @@ extern "C" int ts_adam_step(float* params, const float* grad, float* exp_avg, fl
     adam_kernel<<<grid_for(n), 256, 0, st>>>(params, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), (float)sqrt(bc2), (float)beta1,
                                              (float)beta2, (float)eps, (float)weight_decay, (float)max_grad_norm, norm_scratch, n_partial);
     return tsb::check_launch("ts_adam_step");
+}
+extern "C" int ts_adam_step_dev(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t* step_dev, double lr,
+                                double beta1, double beta2, double eps, double weight_decay, double max_grad_norm,
+                                double* norm_scratch, ts_stream_t stream) {
+    TS_REQUIRE(params && grad && exp_avg && exp_avg_sq && step_dev, "ts_adam_step_dev: bad argument");
+    if (n <= 0) return 0;
+    cudaStream_t st = tsb::as_stream(stream);
+    int n_partial = 0;
+    if (max_grad_norm > 0.0) {
+        TS_REQUIRE(norm_scratch, "ts_adam_step_dev: clipping needs norm_scratch");
+        n_partial = (int)tsb::imin((n + 255) / 256, 256);
+        sumsq_kernel<<<n_partial, 256, 0, st>>>(grad, n, norm_scratch);
+        if (tsb::check_launch("ts_adam_step_dev/norm")) return 1;
+    }
+    adam_dev_kernel<<<grid_for(n), 256, 0, st>>>(params, grad, exp_avg, exp_avg_sq, n, step_dev, lr, beta1, beta2, (float)eps,
+                                                 (float)weight_decay, (float)max_grad_norm, norm_scratch, n_partial);
+    if (tsb::check_launch("ts_adam_step_dev")) return 1;
+    step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+    return tsb::check_launch("ts_adam_step_dev/inc");
 }
 extern "C" int ts_polyak_update(float* target, const float* source, int64_t n, double tau, ts_stream_t stream) {
     TS_REQUIRE(target && source, "ts_polyak_update: null pointer");
