@@ -640,9 +640,13 @@ def offpolicy_extras(dev) -> dict:
             for dst, src in zip(cpu_nets.c[k].parameters(), c.parameters(), strict=True):
                 dst.copy_(src.cpu())
     cpu_nets.c_old = [copy.deepcopy(c) for c in cpu_nets.c]
-    algo = SAC(policy=SACPolicy(actor=actor, action_space=BoxSpace(A)), policy_optim=AdamOptimizerFactory(lr=1e-3), critic=c1,
-               critic_optim=AdamOptimizerFactory(lr=1e-3), critic2=c2, critic2_optim=AdamOptimizerFactory(lr=1e-3), tau=0.005,
-               gamma=0.99, alpha=0.2, n_step_return_horizon=1)
+    graph_nets = copy.deepcopy((actor, c1, c2))
+
+    def make_sac(a, q1, q2, **kw):
+        return SAC(policy=SACPolicy(actor=a, action_space=BoxSpace(A)), policy_optim=AdamOptimizerFactory(lr=1e-3), critic=q1,
+                   critic_optim=AdamOptimizerFactory(lr=1e-3), critic2=q2, critic2_optim=AdamOptimizerFactory(lr=1e-3), tau=0.005,
+                   gamma=0.99, alpha=0.2, n_step_return_horizon=1, **kw)
+    algo = make_sac(actor, c1, c2)
     buf = VectorReplayBuffer(E * steps, E, device=dev, device_mirror=True)
     obs = rng.standard_normal((E, O)).astype(np.float32)
     for _ in range(steps):
@@ -652,6 +656,10 @@ def offpolicy_extras(dev) -> dict:
         obs = nxt
     with policy_within_training_step(algo.policy):
         dt = time_updates(lambda: algo.update(buffer=buf, sample_size=B), 5, 50)
+    algo_g = make_sac(*graph_nets, cuda_graph=True)          # same update, device work replayed from one CUDA graph
+    with policy_within_training_step(algo_g.policy):
+        dt_g = time_updates(lambda: algo_g.update(buffer=buf, sample_size=B), 5, 200)
+    graph_ok = algo_g._graph.get("graph") is not None
     host = dict(obs=np.asarray(buf.obs), act=np.asarray(buf.act), rew=np.asarray(buf.rew), done=np.asarray(buf.done),
                 terminated=np.asarray(buf.terminated), obs_next=np.asarray(buf.obs_next), offset=np.asarray(buf._extend_offset),
                 last_index=np.asarray(buf.last_index), lengths=np.asarray(buf._sizes))
@@ -666,11 +674,13 @@ def offpolicy_extras(dev) -> dict:
         cpu_sac()
     dt_cpu = (time.perf_counter() - t0) / 20
     out["sac"] = {"updates_per_s": 1.0 / dt, "transitions_per_s": B / dt, "ms_per_update": 1e3 * dt,
+                  "cuda_graph": {"updates_per_s": 1.0 / dt_g, "ms_per_update": 1e3 * dt_g, "replaying": bool(graph_ok),
+                                 "note": "SAC(cuda_graph=True): index draw + noise on the host/eager side, everything else one graph replay"},
                   "cpu_port": {"updates_per_s": 1.0 / dt_cpu, "ms_per_update": 1e3 * dt_cpu, "kind": "port (torch CPU, oracle/oracle_offpolicy.py)",
                                "threads": torch.get_num_threads()},
                   "workload": f"SAC.update(sample_size={B}) obs {O} act {A} MLP{list(H)} actor + 2 critics + 2 lagged critics, "
                               f"VectorReplayBuffer {E * steps} transitions with device mirror (BASELINE configs[3] names 4 M), 1 GPU"}
-    del buf, algo
+    del buf, algo, algo_g
 
     # ---- DQN, Atari-shaped (84x84x4 uint8, NatureCNN, PER, 3-step, batch 32; examples/atari/atari_dqn.py:34-49) ----------
     Hh, Ww, NA, B = 84, 84, 6, 32

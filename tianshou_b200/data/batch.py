@@ -755,7 +755,10 @@ class NumpyGlobalPermutationJob:
             self._draw_serially()
             return
         self._key = np.ascontiguousarray(self._st[1], dtype=np.uint32).copy()
-        nw = n_workers or max(1, min(repeat, 4, (os.cpu_count() or 2) // 2))
+        # generator + walker + nw appliers per process; under torchrun every local rank runs its own job on the same host cores
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
+        nw = n_workers or max(1, min(repeat, 4, cores // local_world - 2))
         h = C.c_void_p()
         try:
             call("ts_host_perm_job_start", self._key.ctypes.data_as(C.c_void_p), int(self._st[2]), self._n, repeat,
