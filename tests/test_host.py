@@ -207,6 +207,31 @@ def test_permutation_job_matches_numpy_stream():
         assert np.array_equal(np.random.rand(3), ref_next)
 
 
+@pytest.mark.parametrize("isa", ["scalar", "avx2", "avx512"])
+def test_numpy_permutation_job_every_instruction_set(isa, monkeypatch):
+    """The walker's vector paths (csrc/hostperm_simd.cpp: groups of draws decided by two compares, accepted ones compacted)
+    against np.random.permutation: rows AND the generator state afterwards, from generator positions that start mid-block,
+    over sizes that cross several mask ranges, for repeat > the number of partner-list slots (slot reuse)."""
+    import torch
+
+    from tianshou_b200.data.batch import NumpyGlobalPermutationJob
+    monkeypatch.setenv("TS_B200_PERM_ISA", isa)          # capped by what this CPU has (hostperm_simd.cpp detect_isa)
+    for seed, burn, n, rep in [(10, 0, 31, 2), (11, 5, 33, 3), (12, 623, 64, 2), (13, 700, 4097, 9), (14, 1, 524288, 3),
+                               (15, 17, 99_991, 8)]:
+        np.random.seed(seed)
+        np.random.randint(0, 2**31 - 1, size=burn)            # move the stream position off a block boundary
+        st = np.random.get_state()
+        ref = np.stack([np.random.permutation(n) for _ in range(rep)])
+        ref_next = np.random.rand(3)
+        np.random.set_state(st)
+        rows = torch.empty((rep, n), dtype=torch.int32)
+        with NumpyGlobalPermutationJob(rows, rep, n_workers=3) as job:
+            for r in range(rep):
+                job.wait(r)
+        assert np.array_equal(rows.numpy(), ref), (isa, seed, n)
+        assert np.array_equal(np.random.rand(3), ref_next), (isa, seed, n)
+
+
 def test_vector_buffer_add_slice_path_equals_fancy_path():
     """Lock-step adds (ids = arange) take the strided-slice write; any other id order takes the fancy-indexed write.
     Same buffer contents, same returned (index, ep_return, ep_len, ep_start) rows (manager.py:131-198)."""

@@ -10,8 +10,10 @@
 // swaps of different passes concurrently (~2.5 ms each) straight into the caller's (pinned) int32 rows.
 // Bit-identical to np.random.permutation, including the final generator state (ts_host_perm_job_finish).
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -19,39 +21,30 @@
 #include <vector>
 
 #include "common.cuh"
+#include "hostperm_simd.h"
 
 namespace {
-constexpr int kMtN = 624, kMtM = 397;
-inline void mt_gen(uint32_t* key) {
-    constexpr uint32_t A = 0x9908b0dfu, UP = 0x80000000u, LO = 0x7fffffffu;
-    int i = 0;
-    uint32_t y;
-    for (; i < kMtN - kMtM; ++i) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + kMtM] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
-    for (; i < kMtN - 1; ++i) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + (kMtM - kMtN)] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
-    y = (key[kMtN - 1] & UP) | (key[0] & LO);
-    key[kMtN - 1] = key[kMtM - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
-}
+using tsb_hp::kMtN;
 
-// One generator block: the MT19937 state after its mt_gen (numpy's `key`) and the tempered outputs of its 624 words.
+// One generator block: the MT19937 state after its transition (numpy's `key`) and the tempered outputs of its 624 words.
 struct MtBlock {
     uint32_t key[kMtN];
     uint32_t temp[kMtN];
 };
-__attribute__((target_clones("avx2", "default"))) void mt_temper(const uint32_t* key, uint32_t* out) {
-    for (int d = 0; d < kMtN; ++d) {        // vectorisable: no loop-carried dependence
-        uint32_t y = key[d];
-        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
-        out[d] = y;
-    }
-}
 
 struct PermJob {
     uint32_t key[kMtN];
     int pos = 0;
+    int isa = tsb_hp::detect_isa();
     int64_t n = 0;
     int repeat = 0;
     int32_t* out = nullptr;                      // [repeat][n]
-    std::vector<std::unique_ptr<uint32_t[]>> js; // js[r][i] = accepted j for position i (i >= 1); uninitialised storage
+    // partner lists in walk order (entry k of a pass = the accepted j of position n - 1 - k): kAhead slots of `stride` words, pass r
+    // uses slot r % kAhead.  The storage (and the generator ring) comes from a process-wide cache: a fresh 2 MB-per-slot
+    // allocation costs its page faults on the first pass of every update() otherwise.
+    std::unique_ptr<uint32_t[]> js_store;
+    size_t js_words = 0, stride = 0;
+    uint32_t* js(int r) { return js_store.get() + (size_t)(r % kAhead) * stride; }
     std::vector<int> state;                      // 0 = pending, 1 = walk started (j storage exists), 2 = permutation ready
     std::unique_ptr<std::atomic<int64_t>[]> progress;   // per pass: every position ABOVE this one has its final j (streamed to the applier)
     std::mutex mu;
@@ -60,6 +53,7 @@ struct PermJob {
     std::vector<std::thread> workers;
     std::atomic<int> next_apply{0};
     int applied = 0;                             // passes completely applied (guarded by mu)
+    bool abort_job = false;                      // error path of ts_host_perm_job_start (guarded by mu)
     static constexpr int kAhead = 6;             // the walker stays at most this many passes ahead of the workers
     // generator -> walker ring.  The MT19937 word stream does not depend on how many words a permutation consumes, so a
     // generator thread runs ahead (mt_gen + tempering, vectorised) while the walker does only the data-dependent part
@@ -68,21 +62,24 @@ struct PermJob {
     std::unique_ptr<MtBlock[]> ring;           // uninitialised storage (no 1.3 MB memset per job)
     std::atomic<int64_t> produced{0}, consumed{0};
     std::atomic<bool> stop{false};
+    // TS_B200_PERM_TRACE=1: per-pass stage times (ms since the job started), printed by ts_host_perm_job_finish
+    bool trace = std::getenv("TS_B200_PERM_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    std::vector<double> t_walk0, t_walk1, t_app0, t_app1;
+    double now_ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 
     void generate() {
-        uint32_t k[kMtN];
-        std::memcpy(k, key, sizeof(k));
-        // block 0 = the caller's state as it stands (its words [pos, 624) are unconsumed); block b > 0 = mt_gen of block b - 1
+        // block 0 = the caller's state as it stands (its words [pos, 624) are unconsumed); block b > 0 = the transition of block b - 1
         for (int64_t b = 0;; ++b) {
             while (b - consumed.load(std::memory_order_acquire) >= kRing) {
                 if (stop.load(std::memory_order_acquire)) return;
                 std::this_thread::yield();
             }
             if (stop.load(std::memory_order_acquire)) return;
-            if (b > 0) mt_gen(k);
             MtBlock& blk = ring[(size_t)(b % kRing)];
-            std::memcpy(blk.key, k, sizeof(k));
-            mt_temper(k, blk.temp);
+            if (b == 0) std::memcpy(blk.key, key, sizeof(key));
+            else tsb_hp::mt_next(ring[(size_t)((b - 1) % kRing)].key, blk.key);
+            tsb_hp::mt_temper(blk.key, blk.temp);
             produced.store(b + 1, std::memory_order_release);
         }
     }
@@ -96,48 +93,29 @@ struct PermJob {
         int p = pos;                   // next unconsumed word of it
         const MtBlock* blk = &block(0);
         for (int r = 0; r < repeat; ++r) {
-            {   // back-pressure: bounded memory (4 n bytes per pass in flight) whatever `repeat` is
+            {   // back-pressure: bounded memory (4 n bytes per pass in flight) whatever `repeat` is -- the slot's previous pass is applied
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return r - applied < kAhead; });
+                cv.wait(lk, [&] { return r < kAhead || state[(size_t)(r - kAhead)] == 2 || abort_job; });
+                if (abort_job) break;
             }
-            js[r].reset(new uint32_t[(size_t)(n > 0 ? n : 1)]);
             progress[r].store(n - 1, std::memory_order_relaxed);
             { std::lock_guard<std::mutex> lk(mu); state[r] = 1; }     // the applier may start: it follows `progress`
             cv.notify_all();
-            // One iteration per DRAW (not per position): write the candidate, step to the next position only when it
-            // is accepted (v <= i).  No data-dependent branch -- random_interval's rejection loop mispredicts ~30 % of
-            // the time when written as do/while.  Four draws per bounds check: i drops by at most one per draw.
-            uint32_t* jd = js[r].get();
-            int64_t i = n - 1;
-            while (i >= 1) {
+            // The partner list is in walk order (entry k = position n - 1 - k); tsb_hp::walk decides whole groups of draws
+            // with vector compares (hostperm_simd.cpp).
+            if (trace) t_walk0[(size_t)r] = now_ms();
+            tsb_hp::Walk w{n - 1, js(r)};
+            while (w.i >= 1) {
                 if (p == kMtN) {
                     consumed.store(b + 1, std::memory_order_release);
-                    progress[r].store(i, std::memory_order_release);
+                    progress[r].store(w.i, std::memory_order_release);
                     ++b; p = 0;
                     blk = &block(b);
                 }
-                const uint32_t* tmp = blk->temp + p;
-                const int avail = kMtN - p;
-                int d = 0;
-                while (d < avail && i >= 1) {
-                    // positions i in (lower, mask] share one mask: the loop-carried chain is just compare + subtract
-                    const uint32_t mask = 0xffffffffu >> __builtin_clz((uint32_t)i);
-                    const int64_t lower = (int64_t)(mask >> 1);
-                    for (; d + 4 <= avail && i - 4 > lower; d += 4) {
-                        const uint32_t v0 = tmp[d] & mask;     jd[i] = v0; i -= (int64_t)(v0 <= (uint32_t)i);
-                        const uint32_t v1 = tmp[d + 1] & mask; jd[i] = v1; i -= (int64_t)(v1 <= (uint32_t)i);
-                        const uint32_t v2 = tmp[d + 2] & mask; jd[i] = v2; i -= (int64_t)(v2 <= (uint32_t)i);
-                        const uint32_t v3 = tmp[d + 3] & mask; jd[i] = v3; i -= (int64_t)(v3 <= (uint32_t)i);
-                    }
-                    for (; d < avail && i > lower; ++d) {
-                        const uint32_t v = tmp[d] & mask;
-                        jd[i] = v;
-                        i -= (int64_t)(v <= (uint32_t)i);
-                    }
-                }
-                p += d;
+                p += tsb_hp::walk(isa, blk->temp + p, kMtN - p, &w);
             }
             progress[r].store(0, std::memory_order_release);
+            if (trace) t_walk1[(size_t)r] = now_ms();
         }
         // final generator state = numpy's (key, pos) after these draws: the current block's key, next unconsumed word
         std::memcpy(key, blk->key, sizeof(key));
@@ -150,8 +128,9 @@ struct PermJob {
             if (r >= repeat) return;
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return state[r] >= 1; }); }
             int32_t* o = out + (int64_t)r * n;
+            if (trace) t_app0[(size_t)r] = now_ms();
             for (int64_t i = 0; i < n; ++i) o[i] = (int32_t)i;
-            const uint32_t* j = js[r].get();
+            const uint32_t* j = js(r);
             // The swaps follow the walker as it goes (positions above progress[r] are final): the first pass of an update is
             // ready ~max(walk, apply) after the start instead of walk + apply.  The swap partners are known in advance:
             // prefetch them (the 4 n-byte row does not fit a core's L1; a dependent miss per swap is what this loop would wait on).
@@ -162,15 +141,40 @@ struct PermJob {
                     std::this_thread::yield();
                     safe = progress[r].load(std::memory_order_acquire);
                 }
-                if (i - kPf > safe) __builtin_prefetch(o + j[(size_t)(i - kPf)], 1, 1);
-                const uint32_t v = j[(size_t)i]; const int32_t t = o[v]; o[v] = o[i]; o[i] = t;
+                if (i - kPf > safe) __builtin_prefetch(o + j[(size_t)(n - 1 - (i - kPf))], 1, 1);
+                const uint32_t v = j[(size_t)(n - 1 - i)]; const int32_t t = o[v]; o[v] = o[i]; o[i] = t;
             }
-            js[r].reset();
+            if (trace) t_app1[(size_t)r] = now_ms();
             { std::lock_guard<std::mutex> lk(mu); state[r] = 2; ++applied; }
             cv.notify_all();
         }
     }
 };
+// Storage of the last finished job, kept for the next one (one update() at a time per process is the normal case).
+struct Cache {
+    std::mutex mu;
+    std::unique_ptr<uint32_t[]> js_store;
+    size_t js_words = 0;
+    std::unique_ptr<MtBlock[]> ring;
+};
+Cache& cache() { static Cache c; return c; }
+void take_cached(PermJob* job) {
+    Cache& c = cache();
+    const size_t need = job->stride * (size_t)PermJob::kAhead;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.js_words >= need) { job->js_store = std::move(c.js_store); job->js_words = c.js_words; c.js_words = 0; }
+        job->ring = std::move(c.ring);
+    }
+    if (!job->js_store) { job->js_store.reset(new uint32_t[need]); job->js_words = need; }
+    if (!job->ring) job->ring.reset(new MtBlock[(size_t)PermJob::kRing]);
+}
+void give_back(PermJob* job) {
+    Cache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (job->js_words > c.js_words) { c.js_store = std::move(job->js_store); c.js_words = job->js_words; }
+    if (!c.ring) c.ring = std::move(job->ring);
+}
 }  // namespace
 
 extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t n, int32_t repeat, int32_t* out,
@@ -182,11 +186,12 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
         job = new PermJob();
         std::memcpy(job->key, key, sizeof(job->key));
         job->pos = pos; job->n = n; job->repeat = repeat; job->out = out;
-        job->js.resize((size_t)repeat);
+        job->stride = (size_t)(n > 0 ? n : 1) + tsb_hp::kWalkSlack;
+        take_cached(job);
         job->state.assign((size_t)repeat, 0);
+        for (auto* v : {&job->t_walk0, &job->t_walk1, &job->t_app0, &job->t_app1}) v->assign((size_t)repeat, 0.0);
         job->progress.reset(new std::atomic<int64_t>[(size_t)repeat]);
         for (int r = 0; r < repeat; ++r) job->progress[r].store(n, std::memory_order_relaxed);
-        job->ring.reset(new MtBlock[(size_t)PermJob::kRing]);
         const int nw = n_workers < 1 ? 1 : (n_workers > repeat ? repeat : n_workers);
         job->generator = std::thread([job] { job->generate(); });
         job->producer = std::thread([job] { job->produce(); });
@@ -201,7 +206,7 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
     } catch (const std::exception& e) {     // out of memory / thread limit: the caller falls back to the serial draw
         if (job) {
             // unblock everything before joining: the walker may be waiting on back-pressure with no worker to relieve it
-            { std::lock_guard<std::mutex> lk(job->mu); job->applied = 1 << 30; }
+            { std::lock_guard<std::mutex> lk(job->mu); job->abort_job = true; }
             job->cv.notify_all();
             if (job->producer.joinable()) job->producer.join();
             job->stop.store(true, std::memory_order_release);
@@ -232,6 +237,14 @@ extern "C" int ts_host_perm_job_finish(void* handle, uint32_t* key_out, int32_t*
     for (auto& w : job->workers) w.join();
     std::memcpy(key_out, job->key, sizeof(job->key));
     *pos_out = job->pos;
+    if (job->trace) {
+        fprintf(stderr, "[ts_host_perm] n=%lld repeat=%d isa=%d workers=%zu  (ms since start: walk begin-end | apply begin-end)\n",
+                (long long)job->n, job->repeat, job->isa, job->workers.size());
+        for (int r = 0; r < job->repeat; ++r)
+            fprintf(stderr, "[ts_host_perm]   pass %2d  walk %7.3f-%7.3f  apply %7.3f-%7.3f\n", r, job->t_walk0[(size_t)r],
+                    job->t_walk1[(size_t)r], job->t_app0[(size_t)r], job->t_app1[(size_t)r]);
+    }
+    give_back(job);
     delete job;
     return 0;
 }
