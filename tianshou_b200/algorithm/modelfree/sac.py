@@ -372,7 +372,9 @@ class SAC(OffPolicyAlgorithm):
 
     def _graph_usable(self, buffer: ReplayBuffer) -> bool:
         cols = buffer.device_columns() if hasattr(buffer, "device_columns") else None
+        # (a learning-rate schedule would change a constant baked into the captured launches every update: eager then)
         return (self.cuda_graph and isinstance(self.alpha, FixedAlpha) and not hasattr(buffer, "update_weight") and cols is not None
+                and not self.lr_schedulers
                 and buffer._save_obs_next and all(k in cols for k in ("obs", "act", "rew", "terminated", "done", "obs_next")))
 
     def _device_body(self, buffer: ReplayBuffer, g: dict[str, Any]) -> None:
