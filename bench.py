@@ -336,8 +336,9 @@ def main() -> None:
         dev_batch, dev_idx = algo._sample(buf, 0)
 
         def device_step(a=algo):
-            b = a._preprocess_batch(dev_batch, buf, dev_idx)
-            a._update_with_batch(b, BS, REPEAT)
+            with a._minibatch_order_job(buf, REPEAT):       # what update() does first: the minibatch-order draws start in the background
+                b = a._preprocess_batch(dev_batch, buf, dev_idx)
+                a._update_with_batch(b, BS, REPEAT)
 
         def e2e_step(a=algo):
             a.update(buffer=buf, batch_size=BS, repeat=REPEAT)

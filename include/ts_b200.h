@@ -298,6 +298,8 @@ int ts_clip_adam_step(float* params, float* grad, const float* partials, int32_t
  * same width.  adv_tmp: 32 + 8 * n_minibatch bytes of zero-initialised scratch (double[2] sums, float[2] moments,
  * then one (mean, std) float pair per minibatch).  weight_image: ts_ppo_weight_image_bytes(desc) bytes of scratch
  * (nullable: the kernels then gather + split the weights themselves every step); rebuilt from `params` on entry.
+ * row_feed: NULL, or a feed from ts_host_perm_feed_start whose dev_rows == perm: pass r then waits (on `stream`, not on the
+ * host) until row r of the host permutation job has arrived in `perm`.
  */
 int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, float* exp_avg_sq,
                   int64_t* step_count, const ts_actor_critic_desc* desc, const ts_ppo_hparams* hp,
@@ -307,7 +309,7 @@ int ts_ppo_update(float* params, float* grad, float* partials, float* exp_avg, f
                   float* v_next_tmp, int64_t N, const int32_t* perm, int32_t repeat,
                   const int64_t* bounds /* host */, int32_t n_minibatch, int32_t recompute_adv,
                   double gamma, double lam, double* rms_state, double rms_eps, void* gae_ws,
-                  void* adv_tmp, void* weight_image, float* stats, ts_stream_t stream);
+                  void* adv_tmp, void* weight_image, float* stats, void* row_feed, ts_stream_t stream);
 
 /* ---- multi-GPU fused update: gradient all-reduce INSIDE the epoch kernel over NVLink peer memory -------------
  * Replaces, for one process per GPU (data-parallel replicas, each rank owns its own rollout shard), the
@@ -372,6 +374,16 @@ int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t n, int32_t 
                            void** job_out);
 int ts_host_perm_job_wait(void* job, int32_t r);
 int ts_host_perm_job_finish(void* job, uint32_t* key_out, int32_t* pos_out);
+
+/* Asynchronous feed of a job's rows to the device (replaces the per-pass `perm.to(device)` of a host-driven loop): for
+ * r in [0, repeat) a host function on an internal copy stream blocks that stream until row r is complete, then
+ * host_rows[r] (pinned, the job's `out`) is copied to dev_rows[r] and an event is recorded.  ts_host_perm_feed_wait_row
+ * makes `stream` wait for row r (ts_ppo_update does it before pass r when given the feed), so one asynchronous call enqueues
+ * every pass of an update.  ts_host_perm_feed_finish: after the consumer's work has completed and BEFORE
+ * ts_host_perm_job_finish (the host functions use the job). */
+int ts_host_perm_feed_start(void* job, const int32_t* host_rows, int32_t* dev_rows, int64_t n, int32_t repeat, void** feed_out);
+int ts_host_perm_feed_wait_row(void* feed, int32_t r, ts_stream_t stream);
+int ts_host_perm_feed_finish(void* feed);
 
 /* Device-side minibatch order (opt-in alternative to np.random.permutation, batch.py:1209):
  * out[r*n + i] = pi_r(i), pi_r a keyed bijection of [0,n) (cycle-walking Feistel/Philox). */

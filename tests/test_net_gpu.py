@@ -33,8 +33,9 @@ def test_net_gemm_forward_vs_fp64(M, N, K):
     fp32 = torch.relu(x @ w.T + bias)
     # bf16x3 = 24 significant bits per operand, pieces obtained by truncation: observed 1e-6 .. 3e-6 of max |C| (r2c run)
     e = record_parity(f"net_gemm_fwd/{M}x{N}x{K}", y.cpu().numpy(), ref.cpu().numpy(), rtol=5e-6, atol=5e-6 * float(ref.abs().max()))
-    # fp32-faithful: the same order as torch's own fp32 GEMM against the fp64 product
-    assert e["max_abs_err"] <= 8.0 * float((fp32.double() - ref).abs().max()) + 1e-7
+    # fp32-faithful: the same order as torch's own fp32 GEMM against the fp64 product (plus 2e-6 of max |C|: the fp32
+    # accumulation inside the tensor core over K / 16 x 6 MMAs; torch's N = 1 case is a gemv with a near-exact sum)
+    assert e["max_abs_err"] <= 8.0 * float((fp32.double() - ref).abs().max()) + 2e-6 * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 393, 256), (256, 17, 256), (1568, 576, 64), (100, 40, 33)])
@@ -102,12 +103,15 @@ def test_conv_stack_forward_backward_vs_torch():
     e = record_parity("conv_stack/q_vs_fp64", q.cpu().numpy(), q64.cpu().numpy(), rtol=1e-4, atol=1e-5)
     assert e["max_abs_err"] <= 8.0 * err_torch + 1e-6, (e["max_abs_err"], err_torch)
     coef = torch.randn(B, A, device=DEV)
-    (q_ref * coef).sum().backward()
+    # gradients against autograd in fp64 on the same weights: torch's fp32 convolution backward runs in TF32 on this GPU
+    # (cudnn.allow_tf32 defaults to True; observed 2.6 % of max |grad| away from fp64 on the first layer), so it is no yardstick
+    net64 = __import__("copy").deepcopy(ref_net).double()
+    (net64(x.double()) * coef.double()).sum().backward()
     stack.backward(acts, coef.contiguous(), B, "t")
-    ref_params = [p for m in ref_net.modules() if isinstance(m, (nn.Conv2d, nn.Linear)) for p in (m.weight, m.bias)]
+    ref_params = [p for m in net64.modules() if isinstance(m, (nn.Conv2d, nn.Linear)) for p in (m.weight, m.bias)]
     for i, (p, rp) in enumerate(zip(params, ref_params, strict=True)):
         got = group.view(group.grad, p).view(p.shape)
-        record_parity(f"conv_stack/grad{i}", got.cpu().numpy(), rp.grad.cpu().numpy(), rtol=1e-4,
+        record_parity(f"conv_stack/grad{i}", got.cpu().numpy(), rp.grad.float().cpu().numpy(), rtol=1e-4,
                       atol=2e-5 * float(rp.grad.abs().max()))
 
 

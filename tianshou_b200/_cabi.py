@@ -84,7 +84,7 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_clip_adam_step": [_P, _P, _P, _I32, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams), _P, _P],
     "ts_ppo_update": [_P, _P, _P, _P, _P, _P, C.POINTER(ActorCriticDesc), C.POINTER(PPOHParams),
                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32,
-                      C.POINTER(_I64), _I32, _I32, _D, _D, _P, _D, _P, _P, _P, _P, _P],
+                      C.POINTER(_I64), _I32, _I32, _D, _D, _P, _D, _P, _P, _P, _P, _P, _P],
     "ts_peer_alloc": [_I64, C.POINTER(C.c_void_p), _P],
     "ts_peer_open": [_P, C.POINTER(C.c_void_p)],
     "ts_peer_close": [_P],
@@ -98,6 +98,9 @@ SIGNATURES: dict[str, list[Any]] = {
     "ts_host_perm_job_start": [_P, _I32, _I64, _I32, _P, _I32, C.POINTER(C.c_void_p)],
     "ts_host_perm_job_wait": [_P, _I32],
     "ts_host_perm_job_finish": [_P, _P, C.POINTER(_I32)],
+    "ts_host_perm_feed_start": [_P, _P, _P, _I64, _I32, C.POINTER(C.c_void_p)],
+    "ts_host_perm_feed_wait_row": [_P, _I32, _P],
+    "ts_host_perm_feed_finish": [_P],
     "ts_make_permutation": [C.c_uint64, _I32, _I32, _I64, _P, _P],
     "ts_narrow_i64_i32": [_P, _I64, _P, _P],
     # layered networks of the off-policy algorithms (net_gemm.cu / net_ops.cu)

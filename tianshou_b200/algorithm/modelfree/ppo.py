@@ -18,6 +18,8 @@ stream then differs from the reference's (same distribution, different RNG) -- o
 """
 from __future__ import annotations
 
+import contextlib
+
 import ctypes as C
 from typing import Any, Literal
 
@@ -75,13 +77,20 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         the ``repeat`` permutation draws of ``Batch.split`` (batch.py:1209) are started here, in the background, so that
         they overlap the upload / value pass / GAE that precede the first pass (nothing in between touches numpy's
         global stream: ``sample(0)`` draws nothing)."""
+        with self._minibatch_order_job(buffer, repeat):
+            return super().update(buffer=buffer, batch_size=batch_size, repeat=repeat)
+
+    @contextlib.contextmanager
+    def _minibatch_order_job(self, buffer: Any, repeat: int) -> Any:
+        """Start (and on exit join) the background job that draws this update's ``repeat`` minibatch orders from numpy's
+        global stream.  ``update()`` enters it first thing; ``_update_with_batch`` picks the running job up."""
         job = None
         if (self.minibatch_shuffle == "numpy" and buffer is not None and self.policy.is_within_training_step
                 and len(buffer) > 0 and repeat > 0 and torch.cuda.is_available()):
             job = NumpyGlobalPermutationJob(self._host_perm_rows(repeat, len(buffer)), repeat)
         self._perm_job = job
         try:
-            return super().update(buffer=buffer, batch_size=batch_size, repeat=repeat)
+            yield job
         finally:
             self._perm_job = None
             if job is not None:
@@ -125,6 +134,7 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         stats = self._alloc_stats(repeat * n_mb)
         rank, wsize = self._ranks()
         single_call = self.minibatch_shuffle == "device" and wsize == 1
+        feed = None
 
         if self.minibatch_shuffle == "device":
             perms = ops.make_permutation(self._shuffle_seed, self._shuffle_epoch, repeat, N, dev)
@@ -143,19 +153,52 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
             # pass, so a pending async copy is never overwritten) and overlapped with the GPU work enqueued so far
             job = getattr(self, "_perm_job", None)
             if job is not None and job.shape == (repeat, N):       # started by update(), already running
-                for r in range(repeat):
-                    self._one_pass(batch, job.wait(r).to(dev, non_blocking=True), bounds, hp, stats[r * n_mb:], r, rank, wsize)
+                feed = self._numpy_order_passes(job, batch, bounds, hp, stats, repeat, rank, wsize)
             else:                                                    # _update_with_batch called directly
                 with NumpyGlobalPermutationJob(self._host_perm_rows(repeat, N), repeat) as job:
-                    for r in range(repeat):
-                        self._one_pass(batch, job.wait(r).to(dev, non_blocking=True), bounds, hp, stats[r * n_mb:], r, rank, wsize)
-        result = self._stats_from_device(stats)   # the only host sync of the update
+                    feed = self._numpy_order_passes(job, batch, bounds, hp, stats, repeat, rank, wsize)
+                    if feed is not None:                             # the job must outlive its feed
+                        torch.cuda.current_stream(dev).synchronize()
+                        call("ts_host_perm_feed_finish", feed)
+                        feed = None
+        try:
+            result = self._stats_from_device(stats)   # the only host sync of the update
+        finally:
+            if feed is not None:
+                torch.cuda.current_stream(dev).synchronize()
+                call("ts_host_perm_feed_finish", feed)
         self._rms_end()
         self._flat.export_state(self.optim._optim)
         return result
 
+    def _numpy_order_passes(self, job: NumpyGlobalPermutationJob, batch: Batch, bounds: list[tuple[int, int]], hp: Any,
+                            stats: torch.Tensor, repeat: int, rank: int, wsize: int) -> Any:
+        """All passes in the order of the running host job.  One GPU: ONE asynchronous C call -- the rows reach the device
+        through the job's feed (``ts_host_perm_feed_*``: copy stream + events), the host does not wait for any of them; returns
+        the feed handle, to be finished after the update's final sync.  Several GPUs: pass by pass (the exchange set-up is
+        host-driven), each row uploaded as soon as it is complete."""
+        dev, N, n_mb = self.device, batch.obs.shape[0], len(bounds)
+        if wsize > 1:
+            for r in range(repeat):
+                self._one_pass(batch, job.wait(r).to(dev, non_blocking=True), bounds, hp, stats[r * n_mb:], r, rank, wsize)
+            return None
+        perms = self._buf("perms_dev", (repeat, N), torch.int32)
+        if job._job is None:                 # no background job (foreign bit generator): the rows are complete already
+            perms.copy_(job._rows[:repeat], non_blocking=True)
+            self._device_passes(batch, perms, bounds, hp, stats, repeat, self.recompute_adv)
+            return None
+        feed = C.c_void_p()
+        call("ts_host_perm_feed_start", job._job, C.c_void_p(job._rows.data_ptr()), ptr(perms), N, repeat, C.byref(feed))
+        try:
+            self._device_passes(batch, perms, bounds, hp, stats, repeat, self.recompute_adv, feed=feed)
+        except BaseException:
+            torch.cuda.current_stream(dev).synchronize()
+            call("ts_host_perm_feed_finish", feed)
+            raise
+        return feed
+
     def _device_passes(self, batch: Batch, perm_rows: torch.Tensor | None, bounds: list[tuple[int, int]], hp: Any,
-                       stats: torch.Tensor, nrep: int, recompute: bool) -> None:
+                       stats: torch.Tensor, nrep: int, recompute: bool, feed: Any = None) -> None:
         """``nrep`` passes over the minibatches as ONE asynchronous C call (``ts_ppo_update``): per pass an
         optional critic + GAE recompute and one persistent launch covering every optimiser step."""
         f, dev = self._flat, self.device
@@ -170,7 +213,7 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
              ptr(self._buf("v_next", N, torch.float32)), N, ptr(perm_rows), nrep, bounds_c, n_mb,
              int(recompute), float(self.gamma), float(self.gae_lambda),
              ptr(self._rms_device()) if self.return_scaling else None, float(self._eps),
-             ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(f.weight_image), ptr(stats), stream_ptr(dev))
+             ptr(self._gae_workspace(N)), ptr(adv_tmp), ptr(f.weight_image), ptr(stats), feed, stream_ptr(dev))
 
     # ------------------------------------------------------------------ multi-GPU, fused (NVLink peer memory)
     def _peer_exchange(self, bounds: list[tuple[int, int]]):

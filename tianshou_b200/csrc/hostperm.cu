@@ -229,6 +229,81 @@ extern "C" int ts_host_perm_job_wait(void* handle, int32_t r) {
     return 0;
 }
 
+// ---- asynchronous feed of the job's rows to the device -------------------------------------------------------------
+// The host never has to stand between the walker / appliers and the GPU: for every pass a host function on an internal copy
+// stream blocks THAT STREAM until the row is complete, the row is copied to the device and an event is recorded; the update
+// (ts_ppo_update with `row_feed`) waits for event r on its own stream before pass r.  All passes of an update are then
+// enqueued by ONE asynchronous C call, exactly as with a device-generated order.
+namespace {
+struct RowFeed {
+    struct Arg { PermJob* job; int r; };
+    std::vector<Arg> args;
+    std::vector<cudaEvent_t> ev;
+    cudaStream_t copy_stream = nullptr;
+};
+void CUDART_CB feed_wait_row(void* p) {      // runs on a driver thread: no CUDA calls in here
+    auto* a = static_cast<RowFeed::Arg*>(p);
+    std::unique_lock<std::mutex> lk(a->job->mu);
+    a->job->cv.wait(lk, [&] { return a->job->state[(size_t)a->r] == 2; });
+}
+cudaStream_t feed_stream() {
+    static cudaStream_t streams[tsb::kMaxDevices] = {};
+    static std::mutex mu;
+    const int dev = tsb::device_ordinal();
+    std::lock_guard<std::mutex> lk(mu);
+    if (streams[dev] == nullptr && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return streams[dev];
+}
+}  // namespace
+
+extern "C" int ts_host_perm_feed_start(void* handle, const int32_t* host_rows, int32_t* dev_rows, int64_t n, int32_t repeat,
+                                       void** feed_out) {
+    PermJob* job = static_cast<PermJob*>(handle);
+    TS_REQUIRE(job && host_rows && dev_rows && feed_out && n == job->n && repeat >= 1 && repeat <= job->repeat,
+               "ts_host_perm_feed_start: bad arguments");
+    cudaStream_t cs = feed_stream();
+    TS_REQUIRE(cs != nullptr, "ts_host_perm_feed_start: cannot create the copy stream");
+    auto* feed = new RowFeed();
+    feed->copy_stream = cs;
+    feed->args.resize((size_t)repeat);
+    feed->ev.assign((size_t)repeat, nullptr);
+    auto fail = [&](const char* what, cudaError_t e) {
+        tsb::set_error("ts_host_perm_feed_start: %s: %s", what, cudaGetErrorString(e));
+        cudaStreamSynchronize(cs);          // host functions already enqueued reference feed->args
+        for (cudaEvent_t ev : feed->ev) if (ev) cudaEventDestroy(ev);
+        delete feed;
+        return 1;
+    };
+    for (int r = 0; r < repeat; ++r) {
+        feed->args[(size_t)r] = {job, r};
+        cudaError_t e = cudaEventCreateWithFlags(&feed->ev[(size_t)r], cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail("cudaEventCreate", e);
+        if ((e = cudaLaunchHostFunc(cs, feed_wait_row, &feed->args[(size_t)r])) != cudaSuccess) return fail("cudaLaunchHostFunc", e);
+        if ((e = cudaMemcpyAsync(dev_rows + (int64_t)r * n, host_rows + (int64_t)r * n, (size_t)n * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, cs)) != cudaSuccess) return fail("cudaMemcpyAsync", e);
+        if ((e = cudaEventRecord(feed->ev[(size_t)r], cs)) != cudaSuccess) return fail("cudaEventRecord", e);
+    }
+    *feed_out = feed;
+    return 0;
+}
+
+extern "C" int ts_host_perm_feed_wait_row(void* handle, int32_t r, ts_stream_t stream) {
+    auto* feed = static_cast<RowFeed*>(handle);
+    TS_REQUIRE(feed && r >= 0 && r < (int32_t)feed->ev.size(), "ts_host_perm_feed_wait_row: bad arguments");
+    TS_CUDA(cudaStreamWaitEvent(tsb::as_stream(stream), feed->ev[(size_t)r], 0));
+    return 0;
+}
+
+extern "C" int ts_host_perm_feed_finish(void* handle) {
+    auto* feed = static_cast<RowFeed*>(handle);
+    TS_REQUIRE(feed, "ts_host_perm_feed_finish: bad arguments");
+    const cudaError_t e = cudaStreamSynchronize(feed->copy_stream);      // every host function has returned: `args` may go
+    for (cudaEvent_t ev : feed->ev) if (ev) cudaEventDestroy(ev);
+    delete feed;
+    if (e != cudaSuccess) { tsb::set_error("ts_host_perm_feed_finish: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
 extern "C" int ts_host_perm_job_finish(void* handle, uint32_t* key_out, int32_t* pos_out) {
     PermJob* job = static_cast<PermJob*>(handle);
     TS_REQUIRE(job && key_out && pos_out, "ts_host_perm_job_finish: bad arguments");

@@ -1038,7 +1038,7 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
                              int64_t N, const int32_t* perm, int32_t repeat, const int64_t* bounds,
                              int32_t n_minibatch, int32_t recompute_adv, double gamma, double lam,
                              double* rms_state, double rms_eps, void* gae_ws, void* adv_tmp,
-                             void* weight_image, float* stats, ts_stream_t stream) {
+                             void* weight_image, float* stats, void* row_feed, ts_stream_t stream) {
     if (check_desc(desc, "ts_ppo_update")) return 2;
     TS_REQUIRE(hp && bounds && stats && partials && grad && repeat >= 0 && n_minibatch >= 0, "ts_ppo_update: bad arguments");
     TS_REQUIRE(!hp->advantage_normalization || adv_tmp, "ts_ppo_update: adv_tmp required");
@@ -1063,6 +1063,9 @@ extern "C" int ts_ppo_update(float* params, float* grad, float* partials, float*
         }
         const int32_t* pr = perm ? perm + (int64_t)r * N : nullptr;
         float* rows = stats + (int64_t)r * n_minibatch * TS_PPO_STATS_STRIDE;
+        if (row_feed) {      // row r of `perm` arrives from a host permutation job: the recompute above did not need it
+            if (int e = ts_host_perm_feed_wait_row(row_feed, r, stream)) return e;
+        }
         if (fused && regular) {   // ONE persistent launch for all optimiser steps of this pass
             const int64_t end = bounds[2 * n_minibatch - 1];
             if (hp->advantage_normalization) {
