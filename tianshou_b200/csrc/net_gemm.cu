@@ -63,15 +63,17 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t& w0, ui
 // Stage one 128 (mn) x 64 (k) chunk of an operand.  Shared-memory matrix = [rows = non-contiguous dim][cols =
 // contiguous dim]: K-major -> [128 mn][64 k] (RS = 1024), MN-major -> [64 k][128 mn] (RS = 2048); one task = 8
 // contiguous floats -> one 16-byte chunk per piece.  1024 tasks / 256 threads.
-__device__ __forceinline__ void stage_operand(uint8_t* sm0, uint32_t base, const Operand& op, int mn0, int k0, int k_end) {
+// The global loads of BOTH operands of a chunk are issued before any of them is consumed (one round trip per chunk, not two).
+struct Staged { float v[4][8]; };
+__device__ __forceinline__ void load_operand(Staged& s, const Operand& op, int mn0, int k0, int k_end) {
     const bool vec_ok = ((op.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(op.p) & 15u) == 0);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const int task = (int)threadIdx.x + u * kThreads;
-        int mn, k, r, c0;
-        if (!op.mn_major) { r = task >> 3; c0 = (task & 7) * 8; mn = mn0 + r; k = k0 + c0; }
-        else              { r = task >> 4; c0 = (task & 15) * 8; k = k0 + r; mn = mn0 + c0; }
-        float v[8];
+        int mn, k;
+        if (!op.mn_major) { mn = mn0 + (task >> 3); k = k0 + (task & 7) * 8; }
+        else              { k = k0 + (task >> 4); mn = mn0 + (task & 15) * 8; }
+        float* v = s.v[u];
         // contiguous run of 8 along the fast dimension; `lim` = first invalid index of that dimension
         const int fast = op.mn_major ? mn : k, lim = op.mn_major ? op.mn_extent : k_end;
         const bool row_ok = op.mn_major ? (k < k_end) : (mn < op.mn_extent);
@@ -84,10 +86,17 @@ __device__ __forceinline__ void stage_operand(uint8_t* sm0, uint32_t base, const
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = (row_ok && fast + j < lim) ? __ldg(src + j) : 0.0f;
         }
+    }
+}
+__device__ __forceinline__ void store_operand(uint8_t* sm0, uint32_t base, const Staged& s, int mn_major) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int task = (int)threadIdx.x + u * kThreads;
+        const int r = mn_major ? (task >> 4) : (task >> 3), c0 = mn_major ? (task & 15) * 8 : (task & 7) * 8;
         uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split3_pair(v[2 * j], v[2 * j + 1], w0[j], w1[j], w2[j]);
-        const uint32_t RS = op.mn_major ? 2048u : 1024u;
+        for (int j = 0; j < 4; ++j) split3_pair(s.v[u][2 * j], s.v[u][2 * j + 1], w0[j], w1[j], w2[j]);
+        const uint32_t RS = mn_major ? 2048u : 1024u;
         uint8_t* p = sm0 + (base + moff((uint32_t)r, (uint32_t)c0, RS));
         *reinterpret_cast<uint4*>(p) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
         *reinterpret_cast<uint4*>(p + kPartBytes) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
@@ -159,10 +168,13 @@ __global__ void __launch_bounds__(kThreads, 1) net_gemm_kernel(const GemmParams 
     for (int i = 0; i < chunks; ++i) {
         const int st = i & 1;
         const int k0 = kb + i * BK;
+        Staged sa, sb;
+        load_operand(sa, P.a, m0, k0, ke);
+        load_operand(sb, P.b, n0, k0, ke);
         if (i >= 2) { umma::mbar_wait(&s_empty[st], phase[st]); phase[st] ^= 1u; }    // MMAs of chunk i - 2 done with this stage
         const uint32_t a_base = sbase + st * kStageBytes, b_base = a_base + kOperandBytes;
-        stage_operand(sm0, a_base, P.a, m0, k0, ke);
-        stage_operand(sm0, b_base, P.b, n0, k0, ke);
+        store_operand(sm0, a_base, sa, P.a.mn_major);
+        store_operand(sm0, b_base, sb, P.b.mn_major);
         umma::fence_async_smem();
         umma::fence_before_sync();
         __syncthreads();
@@ -263,12 +275,14 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t ld, int M, in
 namespace tsb {
 
 size_t net_gemm_workspace_floats(int M, int N, int K, int* splits_out) {
-    // split-K when the output has few tiles and K is long (weight gradients over im2col rows)
+    // split-K whenever the output tiles alone leave most SMs idle: weight gradients over im2col rows (K = tens of thousands),
+    // and every layer of a batch-256 MLP (4 output tiles, 4 .. 7 chunks: a lone CTA per tile walks them one round trip after
+    // the other -- 30 .. 57 us under ncu, profiles/r2d_net_gemm_ncu.md -- while 144 SMs idle)
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int chunks = (K + BK - 1) / BK;
     int splits = 1;
-    if (chunks >= 8 && tiles < 64) {
-        splits = (int)imin((int64_t)((148 + tiles - 1) / tiles), (int64_t)(chunks / 2));
+    if (chunks >= 2 && tiles < 64) {
+        splits = (int)imin((int64_t)((148 + tiles - 1) / tiles), (int64_t)chunks);
         if (splits < 1) splits = 1;
     }
     if (splits_out) *splits_out = splits;
