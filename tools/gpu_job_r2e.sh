@@ -14,3 +14,4 @@ print("offpolicy", json.dumps(d.get("offpolicy"))[:400])
 PY
 tail -3 gpurun_out/r2e_bench.err
 grep "pass  [09]" gpurun_out/r2e_bench_trace.err | tail -8
+timeout 120 python tools/host_pass_trace.py > gpurun_out/r2e_host_pass_trace.txt 2>&1; tail -14 gpurun_out/r2e_host_pass_trace.txt
