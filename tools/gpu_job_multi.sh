@@ -19,4 +19,4 @@ for f in ("weak", "strong_c5", "strong_c2"):
         print(f, "failed", e)
 PY
 tail -3 gpurun_out/r2_bench_weak_n${N}.err
-if [ "$N" = "2" ]; then timeout 120 python tools/host_pass_trace.py > gpurun_out/r2_host_pass_trace.txt 2>&1; tail -14 gpurun_out/r2_host_pass_trace.txt; fi
+
