@@ -176,21 +176,26 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         """All passes in the order of the running host job.  One GPU: ONE asynchronous C call -- the rows reach the device
         through the job's feed (``ts_host_perm_feed_*``: copy stream + events), the host does not wait for any of them; returns
         the feed handle, to be finished after the update's final sync.  Several GPUs: pass by pass (the exchange set-up is
-        host-driven), each row uploaded as soon as it is complete."""
+        host-driven), each pass ordered after its row's event on the stream."""
         dev, N, n_mb = self.device, batch.obs.shape[0], len(bounds)
-        if wsize > 1:
-            for r in range(repeat):
-                self._one_pass(batch, job.wait(r).to(dev, non_blocking=True), bounds, hp, stats[r * n_mb:], r, rank, wsize)
-            return None
         perms = self._buf("perms_dev", (repeat, N), torch.int32)
         if job._job is None:                 # no background job (foreign bit generator): the rows are complete already
             perms.copy_(job._rows[:repeat], non_blocking=True)
-            self._device_passes(batch, perms, bounds, hp, stats, repeat, self.recompute_adv)
+            if wsize > 1:
+                for r in range(repeat):
+                    self._one_pass(batch, perms[r], bounds, hp, stats[r * n_mb:], r, rank, wsize)
+            else:
+                self._device_passes(batch, perms, bounds, hp, stats, repeat, self.recompute_adv)
             return None
         feed = C.c_void_p()
         call("ts_host_perm_feed_start", job._job, C.c_void_p(job._rows.data_ptr()), ptr(perms), N, repeat, C.byref(feed))
         try:
-            self._device_passes(batch, perms, bounds, hp, stats, repeat, self.recompute_adv, feed=feed)
+            if wsize > 1:      # pass by pass (the exchange set-up is host-driven), but the STREAM waits for row r, not the host
+                for r in range(repeat):
+                    call("ts_host_perm_feed_wait_row", feed, r, stream_ptr(dev))
+                    self._one_pass(batch, perms[r], bounds, hp, stats[r * n_mb:], r, rank, wsize)
+            else:
+                self._device_passes(batch, perms, bounds, hp, stats, repeat, self.recompute_adv, feed=feed)
         except BaseException:
             torch.cuda.current_stream(dev).synchronize()
             call("ts_host_perm_feed_finish", feed)
