@@ -78,10 +78,16 @@ def test_two_rank_update_matches_reference(variant, path, tmp_path):
 @pytest.mark.parametrize("variant", ["A", "B"])
 def test_two_rank_shared_rollout_matches_reference(variant, tmp_path):
     """Strong scaling: ONE rollout, the same ``np.random.permutation`` stream on both ranks, every minibatch split
-    into two contiguous slices, gradient sum inside the epoch kernel -> the reference run's results, loss table row by row."""
+    into two contiguous slices, gradient sum inside the epoch kernel -> the reference run's results, loss table row by row.
+    Variant B's golden uses a minibatch size that does not divide the rollout (ragged last minibatch): a shared rollout
+    refuses that split loudly (``ValueError`` from ``PPO._shared_slice``) instead of changing the minibatch composition."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
+    if variant == "B":
+        with pytest.raises(Exception, match="rollout_partition='shared' needs"):
+            mp.spawn(_worker, args=(2, _free_port(), variant, "p2p", str(tmp_path), "shared"), nprocs=2, join=True)
+        return
     mp.spawn(_worker, args=(2, _free_port(), variant, "p2p", str(tmp_path), "shared"), nprocs=2, join=True)
     a, b = torch.load(tmp_path / "flat0.pt"), torch.load(tmp_path / "flat1.pt")
     assert torch.equal(a, b), "replicas diverged"

@@ -13,7 +13,7 @@ python - <<PY
 import json
 for f in ("weak", "strong_c5", "strong_c2"):
     try:
-        d = json.load(open(f"gpurun_out/r2_bench_{f}_n$N.json"))
+        d = json.loads([l for l in open(f"gpurun_out/r2_bench_{f}_n$N.json") if l.startswith("{")][-1])
         print(f, d["n_gpus"], "value", round(d["value"] / 1e6, 2), "M/s", round(d["ms_per_step"], 2), "ms; e2e", round(d["e2e"]["value"] / 1e6, 2), "dev-order", round(d["value_device_order"]["value"] / 1e6, 2), d.get("multi_gpu_check"), (d.get("config4") or {}).get("value"))
     except Exception as e:
         print(f, "failed", e)
