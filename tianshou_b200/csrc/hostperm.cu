@@ -15,10 +15,14 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
+
+#include <pthread.h>
 
 #include "common.cuh"
 #include "hostperm_simd.h"
@@ -30,6 +34,51 @@ using tsb_hp::kMtN;
 struct MtBlock {
     uint32_t key[kMtN];
     uint32_t temp[kMtN];
+};
+
+// Threads parked between jobs: creating the six threads of a job costs ~0.3 ms at the top of every update() (measured on
+// the GPU box, profiles/r2g_default_order_hosttrace.txt), waking parked ones a few tens of microseconds.  A task gets a
+// parked thread if one is free, else a new thread (tasks of one job depend on each other: none may queue behind another).
+class Crew {
+  public:
+    static Crew& get() {
+        static std::once_flag once;
+        std::call_once(once, [] { pthread_atfork(nullptr, nullptr, [] { instance() = nullptr; }); });
+        Crew*& c = instance();
+        if (c == nullptr) c = new Crew();        // never destroyed: parked threads may outlive static destructors
+        return *c;
+    }
+    void run(std::function<void()> f) {
+        std::unique_lock<std::mutex> lk(mu_);
+        q_.push_back(std::move(f));
+        if ((size_t)idle_ >= q_.size()) { cv_.notify_one(); return; }
+        try {
+            std::thread([this] { loop(); }).detach();
+        } catch (...) {
+            q_.pop_back();
+            throw;
+        }
+    }
+  private:
+    static Crew*& instance() { static Crew* c = nullptr; return c; }
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                ++idle_;
+                cv_.wait(lk, [&] { return !q_.empty(); });
+                --idle_;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    int idle_ = 0;
 };
 
 struct PermJob {
@@ -49,8 +98,8 @@ struct PermJob {
     std::unique_ptr<std::atomic<int64_t>[]> progress;   // per pass: every position ABOVE this one has its final j (streamed to the applier)
     std::mutex mu;
     std::condition_variable cv;
-    std::thread generator, producer;
-    std::vector<std::thread> workers;
+    int live = 0;                                // tasks of this job still running on crew threads (guarded by mu)
+    int n_appliers = 0;
     std::atomic<int> next_apply{0};
     int applied = 0;                             // passes completely applied (guarded by mu)
     bool abort_job = false;                      // error path of ts_host_perm_job_start (guarded by mu)
@@ -68,6 +117,27 @@ struct PermJob {
     std::vector<double> t_walk0, t_walk1, t_app0, t_app1;
     double now_ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
 
+    // Run a member task on a crew thread; `live` counts the tasks still running (the last decrement happens under `mu`, so
+    // the finisher, who waits under the same mutex, cannot free the job while a task still touches it).
+    template <class F> void launch(F f) {
+        { std::lock_guard<std::mutex> lk(mu); ++live; }
+        try {
+            Crew::get().run([this, f] {
+                f();
+                std::lock_guard<std::mutex> lk(mu);
+                --live;
+                cv.notify_all();
+            });
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(mu);
+            --live;
+            throw;
+        }
+    }
+    void wait_all_tasks() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return live == 0; });
+    }
     void generate() {
         // block 0 = the caller's state as it stands (its words [pos, 624) are unconsumed); block b > 0 = the transition of block b - 1
         for (int64_t b = 0;; ++b) {
@@ -182,6 +252,7 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
     TS_REQUIRE(key && out && job_out && n >= 0 && n <= 0x7fffffffLL && repeat >= 1 && pos >= 0 && pos <= kMtN,
                "ts_host_perm_job_start: bad arguments");
     PermJob* job = nullptr;
+    bool walker_launched = false;
     try {
         job = new PermJob();
         std::memcpy(job->key, key, sizeof(job->key));
@@ -193,13 +264,15 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
         job->progress.reset(new std::atomic<int64_t>[(size_t)repeat]);
         for (int r = 0; r < repeat; ++r) job->progress[r].store(n, std::memory_order_relaxed);
         const int nw = n_workers < 1 ? 1 : (n_workers > repeat ? repeat : n_workers);
-        job->generator = std::thread([job] { job->generate(); });
-        job->producer = std::thread([job] { job->produce(); });
+        job->launch([job] { job->generate(); });
+        job->launch([job] { job->produce(); });
+        walker_launched = true;
         for (int w = 0; w < nw; ++w) {
             try {
-                job->workers.emplace_back([job] { job->apply_loop(); });
+                job->launch([job] { job->apply_loop(); });
+                ++job->n_appliers;
             } catch (const std::exception&) {
-                if (job->workers.empty()) throw;      // no worker at all: give up; otherwise run with fewer
+                if (job->n_appliers == 0) throw;      // no applier at all: give up; otherwise run with fewer
                 break;
             }
         }
@@ -208,10 +281,9 @@ extern "C" int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t 
             // unblock everything before joining: the walker may be waiting on back-pressure with no worker to relieve it
             { std::lock_guard<std::mutex> lk(job->mu); job->abort_job = true; }
             job->cv.notify_all();
-            if (job->producer.joinable()) job->producer.join();
-            job->stop.store(true, std::memory_order_release);
-            if (job->generator.joinable()) job->generator.join();
-            for (auto& w : job->workers) w.join();
+            // the walker leaves through abort_job and then stops the generator itself (it may still need words until then)
+            if (!walker_launched) job->stop.store(true, std::memory_order_release);
+            job->wait_all_tasks();
             delete job;
         }
         tsb::set_error("ts_host_perm_job_start: %s", e.what());
@@ -307,14 +379,12 @@ extern "C" int ts_host_perm_feed_finish(void* handle) {
 extern "C" int ts_host_perm_job_finish(void* handle, uint32_t* key_out, int32_t* pos_out) {
     PermJob* job = static_cast<PermJob*>(handle);
     TS_REQUIRE(job && key_out && pos_out, "ts_host_perm_job_finish: bad arguments");
-    job->producer.join();
-    job->generator.join();
-    for (auto& w : job->workers) w.join();
+    job->wait_all_tasks();
     std::memcpy(key_out, job->key, sizeof(job->key));
     *pos_out = job->pos;
     if (job->trace) {
         fprintf(stderr, "[ts_host_perm] n=%lld repeat=%d isa=%d workers=%zu  (ms since start: walk begin-end | apply begin-end)\n",
-                (long long)job->n, job->repeat, job->isa, job->workers.size());
+                (long long)job->n, job->repeat, job->isa, (size_t)job->n_appliers);
         for (int r = 0; r < job->repeat; ++r)
             fprintf(stderr, "[ts_host_perm]   pass %2d  walk %7.3f-%7.3f  apply %7.3f-%7.3f\n", r, job->t_walk0[(size_t)r],
                     job->t_walk1[(size_t)r], job->t_app0[(size_t)r], job->t_app1[(size_t)r]);
