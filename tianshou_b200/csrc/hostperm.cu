@@ -14,6 +14,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -23,6 +24,7 @@
 #include <vector>
 
 #include <pthread.h>
+#include <sched.h>
 
 #include "common.cuh"
 #include "hostperm_simd.h"
@@ -81,6 +83,56 @@ class Crew {
     int idle_ = 0;
 };
 
+// NUMA placement: the rows live in pinned host memory allocated by the calling thread; a job whose appliers land on the other
+// socket does its ~5 M dependent random swaps over the inter-socket link (the same job took 6.2 .. 10.8 ms on different
+// visits of a 2-socket box).  The crew threads of a job are confined to the CPUs of the caller's NUMA node (intersected with
+// the process affinity; no pinning if that leaves fewer than 8 CPUs, on a single-node machine, or with TS_B200_PERM_PIN=0).
+struct NodeCpus {
+    bool valid = false;
+    cpu_set_t set;
+};
+inline bool parse_cpulist(const char* s, cpu_set_t* out) {
+    CPU_ZERO(out);
+    bool any = false;
+    while (*s) {
+        char* end = nullptr;
+        const long a = std::strtol(s, &end, 10);
+        if (end == s) break;
+        long b = a;
+        s = end;
+        if (*s == '-') { b = std::strtol(s + 1, &end, 10); s = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, out); any = true; }
+        if (*s == ',') ++s;
+    }
+    return any;
+}
+inline NodeCpus caller_node_cpus() {
+    NodeCpus r;
+    const char* env = std::getenv("TS_B200_PERM_PIN");
+    if (env != nullptr && env[0] == '0') return r;
+    const int cpu = sched_getcpu();
+    if (cpu < 0) return r;
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return r;
+    int nodes_seen = 0;
+    for (int node = 0; node < 64; ++node) {
+        char path[96];
+        std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+        FILE* f = std::fopen(path, "r");
+        if (f == nullptr) continue;
+        ++nodes_seen;
+        char buf[4096];
+        cpu_set_t cpus;
+        const bool ok = std::fgets(buf, sizeof(buf), f) != nullptr && parse_cpulist(buf, &cpus);
+        std::fclose(f);
+        if (!ok || !CPU_ISSET(cpu, &cpus) || r.valid) continue;
+        CPU_AND(&cpus, &cpus, &allowed);
+        if (CPU_COUNT(&cpus) >= 8) { r.valid = true; r.set = cpus; }
+    }
+    if (nodes_seen < 2) r.valid = false;      // one node: nothing to choose
+    return r;
+}
+
 struct PermJob {
     uint32_t key[kMtN];
     int pos = 0;
@@ -98,6 +150,7 @@ struct PermJob {
     std::unique_ptr<std::atomic<int64_t>[]> progress;   // per pass: every position ABOVE this one has its final j (streamed to the applier)
     std::mutex mu;
     std::condition_variable cv;
+    NodeCpus node = caller_node_cpus();          // where the caller (and its pinned rows) live
     int live = 0;                                // tasks of this job still running on crew threads (guarded by mu)
     int n_appliers = 0;
     std::atomic<int> next_apply{0};
@@ -123,6 +176,7 @@ struct PermJob {
         { std::lock_guard<std::mutex> lk(mu); ++live; }
         try {
             Crew::get().run([this, f] {
+                if (node.valid) sched_setaffinity(0, sizeof(node.set), &node.set);      // this thread only
                 f();
                 std::lock_guard<std::mutex> lk(mu);
                 --live;
@@ -383,8 +437,9 @@ extern "C" int ts_host_perm_job_finish(void* handle, uint32_t* key_out, int32_t*
     std::memcpy(key_out, job->key, sizeof(job->key));
     *pos_out = job->pos;
     if (job->trace) {
-        fprintf(stderr, "[ts_host_perm] n=%lld repeat=%d isa=%d workers=%zu  (ms since start: walk begin-end | apply begin-end)\n",
-                (long long)job->n, job->repeat, job->isa, (size_t)job->n_appliers);
+        fprintf(stderr, "[ts_host_perm] n=%lld repeat=%d isa=%d workers=%zu numa_pinned=%d (%d cpus)  (ms since start: walk begin-end | apply begin-end)\n",
+                (long long)job->n, job->repeat, job->isa, (size_t)job->n_appliers, (int)job->node.valid,
+                job->node.valid ? CPU_COUNT(&job->node.set) : 0);
         for (int r = 0; r < job->repeat; ++r)
             fprintf(stderr, "[ts_host_perm]   pass %2d  walk %7.3f-%7.3f  apply %7.3f-%7.3f\n", r, job->t_walk0[(size_t)r],
                     job->t_walk1[(size_t)r], job->t_app0[(size_t)r], job->t_app1[(size_t)r]);
