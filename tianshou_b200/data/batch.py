@@ -758,7 +758,8 @@ class NumpyGlobalPermutationJob:
         # generator + walker + nw appliers per process; under torchrun every local rank runs its own job on the same host cores
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
-        nw = n_workers or max(1, min(repeat, 4, cores // local_world - 2))
+        # a row beyond ~1 M entries no longer fits a core's L2: its swaps cost ~4x as much each, so give the appliers twice the width
+        nw = n_workers or max(1, min(repeat, 8 if self._n >= (1 << 20) else 4, cores // local_world - 2))
         h = C.c_void_p()
         try:
             call("ts_host_perm_job_start", self._key.ctypes.data_as(C.c_void_p), int(self._st[2]), self._n, repeat,
