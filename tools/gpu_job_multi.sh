@@ -7,7 +7,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 if [ "$N" = "2" ]; then python -m pytest tests/test_dist_gpu.py -m gpu -q 2>&1 | tail -15 > gpurun_out/r2_dist_tests_n${N}.txt; else echo "dist tests run in the 2-GPU visit" > gpurun_out/r2_dist_tests_n${N}.txt; fi
 timeout 600 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_bench_weak_n${N}.json 2> gpurun_out/r2_bench_weak_n${N}.err
 timeout 600 $TR bench.py --gpus $N --steps 3 --warmup 3 --scaling strong --config c5 --no-extras > gpurun_out/r2_bench_strong_c5_n${N}.json 2> gpurun_out/r2_bench_strong_c5_n${N}.err
-timeout 600 $TR bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --no-extras > gpurun_out/r2_bench_strong_c2_n${N}.json 2> gpurun_out/r2_bench_strong_c2_n${N}.err
+[ "$N" = "2" ] && timeout 600 $TR bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --no-extras > gpurun_out/r2_bench_strong_c2_n${N}.json 2> gpurun_out/r2_bench_strong_c2_n${N}.err
 cat gpurun_out/r2_dist_tests_n${N}.txt
 python - <<PY
 import json
