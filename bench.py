@@ -421,7 +421,17 @@ def main() -> None:
                     ms5 = timed(step5, 2)
                 np.random.set_state(np_state)
                 n5 = c5["E"] * c5["T"]
+                a5d, _, _ = build_mujoco_ppo(OBS, ACT, dev, minibatch_shuffle="device", rollout_partition="shared")
+                with policy_within_training_step(a5d.policy):
+                    step5d = lambda: a5d.update(buffer=buf5, batch_size=c5["bs"], repeat=REPEAT)   # noqa: E731
+                    step5d()
+                    ms5d = timed(step5d, 2)
+                del a5d
                 config4 = {"value": n5 * 2 / (ms5 / 1e3), "unit": "transitions/s", "ms_per_step": ms5 / 2, "scaling": "strong",
+                           "device_order": {"value": n5 * 2 / (ms5d / 1e3), "ms_per_step": ms5d / 2,
+                                            "note": "same update() with the opt-in device-generated minibatch order: at 2 M transitions "
+                                                    "the reference-exact order is bounded by the sequential MT19937 walk on the host "
+                                                    "(~1.6 ms per 2 M-entry permutation), not by the GPUs"},
                            "n_gpus": world, "config": workload_config(world, "c5", "strong"), "steps": 2, "warmup": 1,
                            "timing": "end to end through update(): host rollout upload + D2H of the loss table inside",
                            "replicas_equal": replicas_equal(a5)}

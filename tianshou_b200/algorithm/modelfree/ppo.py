@@ -85,16 +85,40 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         """Start (and on exit join) the background job that draws this update's ``repeat`` minibatch orders from numpy's
         global stream.  ``update()`` enters it first thing; ``_update_with_batch`` picks the running job up."""
         job = None
-        if (self.minibatch_shuffle == "numpy" and buffer is not None and self.policy.is_within_training_step
-                and len(buffer) > 0 and repeat > 0 and torch.cuda.is_available()):
+        wanted = (self.minibatch_shuffle == "numpy" and buffer is not None and self.policy.is_within_training_step
+                  and len(buffer) > 0 and repeat > 0 and torch.cuda.is_available())
+        # ONE shared rollout on several GPUs: every rank would draw the very same rows from the very same stream.  Rank 0 draws,
+        # the rows travel over NVLink (one broadcast per pass), and the advanced generator state is broadcast at the end.
+        remote = wanted and self._shared_order_from_rank0()
+        if wanted and (not remote or self._ranks()[0] == 0):
             job = NumpyGlobalPermutationJob(self._host_perm_rows(repeat, len(buffer)), repeat)
-        self._perm_job = job
+        self._perm_job = job if not (remote and job is None) else "rank0"
         try:
             yield job
         finally:
             self._perm_job = None
             if job is not None:
                 job.__exit__(None, None, None)      # joins the threads, writes the advanced state back into numpy
+            if remote:
+                self._broadcast_numpy_state()
+
+    def _shared_order_from_rank0(self) -> bool:
+        import torch.distributed as dist
+        return (self.rollout_partition == "shared" and self._ranks()[1] > 1 and dist.is_available() and dist.is_initialized()
+                and dist.get_backend() == "nccl")
+
+    def _broadcast_numpy_state(self) -> None:
+        """numpy's global legacy state of rank 0 -> every rank (they all consumed the same draws: rank 0 made them)."""
+        import torch.distributed as dist
+        st = np.random.get_state()
+        t = torch.zeros(627, dtype=torch.float64, device=self.device)
+        if dist.get_rank() == 0:
+            t[:624] = torch.from_numpy(np.asarray(st[1], dtype=np.float64)).to(self.device)
+            t[624], t[625], t[626] = float(st[2]), float(st[3]), float(st[4])
+        dist.broadcast(t, 0)
+        if dist.get_rank() != 0:
+            h = t.cpu().numpy()
+            np.random.set_state((st[0], h[:624].astype(np.uint32), int(h[624]), int(h[625]), float(h[626])))
 
     def _one_pass(self, batch: Batch, perm_r: torch.Tensor, bounds: list[tuple[int, int]], hp: Any, stats: torch.Tensor,
                   r: int, rank: int, wsize: int) -> None:
@@ -152,7 +176,11 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
             # bit-identical, produced ahead of the passes by background threads straight into pinned memory (one row per
             # pass, so a pending async copy is never overwritten) and overlapped with the GPU work enqueued so far
             job = getattr(self, "_perm_job", None)
-            if job is not None and job.shape == (repeat, N):       # started by update(), already running
+            if isinstance(job, str) or (wsize > 1 and self._shared_order_from_rank0() and job is not None and rank == 0
+                                        and job.shape == (repeat, N)):
+                # shared rollout: rank 0's rows, broadcast pass by pass (job is "rank0" on the other ranks)
+                feed = self._rank0_order_passes(None if isinstance(job, str) else job, batch, bounds, hp, stats, repeat, rank, wsize)
+            elif job is not None and job.shape == (repeat, N):       # started by update(), already running
                 feed = self._numpy_order_passes(job, batch, bounds, hp, stats, repeat, rank, wsize)
             else:                                                    # _update_with_batch called directly
                 with NumpyGlobalPermutationJob(self._host_perm_rows(repeat, N), repeat) as job:
@@ -170,6 +198,33 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         self._rms_end()
         self._flat.export_state(self.optim._optim)
         return result
+
+    def _rank0_order_passes(self, job: NumpyGlobalPermutationJob | None, batch: Batch, bounds: list[tuple[int, int]], hp: Any,
+                            stats: torch.Tensor, repeat: int, rank: int, wsize: int) -> Any:
+        """Shared rollout on several GPUs: rank 0 feeds its job's rows to its device and broadcasts each one (NCCL, on the
+        compute stream, 4 N bytes over NVLink) before the pass that uses it; the other ranks run no host job at all."""
+        import torch.distributed as dist
+        dev, N, n_mb = self.device, batch.obs.shape[0], len(bounds)
+        perms = self._buf("perms_dev", (repeat, N), torch.int32)
+        feed = None
+        if job is not None:
+            if job._job is None:
+                perms.copy_(job._rows[:repeat], non_blocking=True)
+            else:
+                feed = C.c_void_p()
+                call("ts_host_perm_feed_start", job._job, C.c_void_p(job._rows.data_ptr()), ptr(perms), N, repeat, C.byref(feed))
+        try:
+            for r in range(repeat):
+                if feed is not None:
+                    call("ts_host_perm_feed_wait_row", feed, r, stream_ptr(dev))
+                dist.broadcast(perms[r], 0)
+                self._one_pass(batch, perms[r], bounds, hp, stats[r * n_mb:], r, rank, wsize)
+        except BaseException:
+            if feed is not None:
+                torch.cuda.current_stream(dev).synchronize()
+                call("ts_host_perm_feed_finish", feed)
+            raise
+        return feed
 
     def _numpy_order_passes(self, job: NumpyGlobalPermutationJob, batch: Batch, bounds: list[tuple[int, int]], hp: Any,
                             stats: torch.Tensor, repeat: int, rank: int, wsize: int) -> Any:
