@@ -8,6 +8,8 @@ if [ "$N" = "2" ]; then python -m pytest tests/test_dist_gpu.py -m gpu -q 2>&1 |
 timeout 600 $TR bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2_bench_weak_n${N}.json 2> gpurun_out/r2_bench_weak_n${N}.err
 timeout 600 $TR bench.py --gpus $N --steps 3 --warmup 3 --scaling strong --config c5 --no-extras > gpurun_out/r2_bench_strong_c5_n${N}.json 2> gpurun_out/r2_bench_strong_c5_n${N}.err
 [ "$N" = "2" ] && timeout 600 $TR bench.py --gpus $N --steps 5 --warmup 3 --scaling strong --no-extras > gpurun_out/r2_bench_strong_c2_n${N}.json 2> gpurun_out/r2_bench_strong_c2_n${N}.err
+TS_B200_PERM_TRACE=1 timeout 300 $TR bench.py --gpus $N --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2_bench_weak_trace_n${N}.json 2> gpurun_out/r2_bench_weak_trace_n${N}.err
+grep "pass  [0-3]" gpurun_out/r2_bench_weak_trace_n${N}.err | tail -32 | sort | uniq -c | tail -12
 cat gpurun_out/r2_dist_tests_n${N}.txt
 python - <<PY
 import json
