@@ -160,7 +160,7 @@ struct PermJob {
     // generator -> walker ring.  The MT19937 word stream does not depend on how many words a permutation consumes, so a
     // generator thread runs ahead (mt_gen + tempering, vectorised) while the walker does only the data-dependent part
     // (mask, compare, advance): ~0.7 ms per 524 288-element permutation instead of ~1.7 ms in one thread.
-    static constexpr int64_t kRing = 1024;       // blocks (5 KB each): the generator may run ~640 k words (about one pass) ahead
+    static constexpr int64_t kRing = 256;        // blocks (5 KB each): the generator may run ~160 k words ahead
     std::unique_ptr<MtBlock[]> ring;           // uninitialised storage (no 1.3 MB memset per job)
     std::atomic<int64_t> produced{0}, consumed{0};
     std::atomic<bool> stop{false};
@@ -195,12 +195,9 @@ struct PermJob {
     void generate() {
         // block 0 = the caller's state as it stands (its words [pos, 624) are unconsumed); block b > 0 = the transition of block b - 1
         for (int64_t b = 0;; ++b) {
-            // the generator is ~2x faster than the walker: most of the time the ring is full.  Sleep then (a full ring is
-            // ~350 us of walker work), do not spin: with eight ranks on one box a spinning generator per rank takes a
-            // hardware thread away from somebody's walker or applier.
             while (b - consumed.load(std::memory_order_acquire) >= kRing) {
                 if (stop.load(std::memory_order_acquire)) return;
-                std::this_thread::sleep_for(std::chrono::microseconds(30));
+                std::this_thread::yield();
             }
             if (stop.load(std::memory_order_acquire)) return;
             MtBlock& blk = ring[(size_t)(b % kRing)];
