@@ -39,7 +39,7 @@ def main():
     import numpy as np
     P = int(sys.argv[1]) if len(sys.argv) > 1 else 8
     ctx = mp.get_context("spawn")
-    for nw in (4, 2, 1):
+    for nw in ((4,) if len(sys.argv) > 2 else (4, 2, 1)):
         for pin in (True, False):
             q = ctx.Queue()
             start_at = time.time() + 25.0          # after every process has imported torch
