@@ -25,6 +25,9 @@
 
 #include <pthread.h>
 #include <sched.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include "common.cuh"
 #include "hostperm_simd.h"
@@ -151,6 +154,8 @@ struct PermJob {
     std::mutex mu;
     std::condition_variable cv;
     NodeCpus node = caller_node_cpus();          // where the caller (and its pinned rows) live
+    // TS_B200_PERM_NICE=<n>: run the crew at a lower priority than the thread that feeds the GPU (several ranks per box)
+    int nice_value = [] { const char* e = std::getenv("TS_B200_PERM_NICE"); return e ? std::atoi(e) : 0; }();
     int live = 0;                                // tasks of this job still running on crew threads (guarded by mu)
     int n_appliers = 0;
     std::atomic<int> next_apply{0};
@@ -177,6 +182,7 @@ struct PermJob {
         try {
             Crew::get().run([this, f] {
                 if (node.valid) sched_setaffinity(0, sizeof(node.set), &node.set);      // this thread only
+                if (nice_value != 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), nice_value);   // per-thread on Linux
                 f();
                 std::lock_guard<std::mutex> lk(mu);
                 --live;

@@ -759,7 +759,8 @@ class NumpyGlobalPermutationJob:
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
         # a row beyond ~1 M entries no longer fits a core's L2: its swaps cost ~4x as much each, so give the appliers twice the width
-        nw = n_workers or max(1, min(repeat, 8 if self._n >= (1 << 20) else 4, cores // local_world - 2))
+        nw = (n_workers or int(os.environ.get("TS_B200_PERM_WORKERS", "0") or 0)
+              or max(1, min(repeat, 8 if self._n >= (1 << 20) else 4, cores // local_world - 2)))
         h = C.c_void_p()
         try:
             call("ts_host_perm_job_start", self._key.ctypes.data_as(C.c_void_p), int(self._st[2]), self._n, repeat,
