@@ -155,7 +155,12 @@ struct PermJob {
     std::condition_variable cv;
     NodeCpus node = caller_node_cpus();          // where the caller (and its pinned rows) live
     // TS_B200_PERM_NICE=<n>: run the crew at a lower priority than the thread that feeds the GPU (several ranks per box)
-    int nice_value = [] { const char* e = std::getenv("TS_B200_PERM_NICE"); return e ? std::atoi(e) : 0; }();
+    // (default: 10 when torchrun started >= 4 local ranks -- measured at N = 4, profiles/r2_ab_n4.txt -- else 0)
+    int nice_value = [] {
+        if (const char* e = std::getenv("TS_B200_PERM_NICE")) return std::atoi(e);
+        const char* w = std::getenv("LOCAL_WORLD_SIZE");
+        return (w != nullptr && std::atoi(w) >= 4) ? 10 : 0;
+    }();
     int live = 0;                                // tasks of this job still running on crew threads (guarded by mu)
     int n_appliers = 0;
     std::atomic<int> next_apply{0};

@@ -760,7 +760,9 @@ class NumpyGlobalPermutationJob:
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
         # a row beyond ~1 M entries no longer fits a core's L2: its swaps cost ~4x as much each, so give the appliers twice the width
         nw = (n_workers or int(os.environ.get("TS_B200_PERM_WORKERS", "0") or 0)
-              or max(1, min(repeat, 8 if self._n >= (1 << 20) else 4, cores // local_world - 2)))
+              or max(1, min(repeat, 8 if self._n >= (1 << 20) else (2 if local_world >= 4 else 4), cores // local_world - 2)))
+        # (>= 4 local ranks: two appliers per rank still finish every row ahead of the GPU and leave the host threads that feed the
+        # GPUs more room -- weak scaling at N = 4: 15.0 ms per update against 15.8 with four, profiles/r2_ab_n4.txt)
         h = C.c_void_p()
         try:
             call("ts_host_perm_job_start", self._key.ctypes.data_as(C.c_void_p), int(self._st[2]), self._n, repeat,
