@@ -232,6 +232,54 @@ def test_numpy_permutation_job_every_instruction_set(isa, monkeypatch):
         assert np.array_equal(np.random.rand(3), ref_next), (isa, seed, n)
 
 
+def test_numpy_permutation_job_many_jobs_and_fork():
+    """The job's threads are parked between jobs (csrc/hostperm.cu Crew) and its scratch storage is cached: many jobs in a row,
+    two jobs alive at the same time (the second gets fresh threads / storage), and a job in a forked child (the parked threads
+    do not exist there: the crew is rebuilt) all reproduce numpy's stream."""
+    import torch
+
+    from tianshou_b200.data.batch import NumpyGlobalPermutationJob
+
+    def check(seed, n, rep):
+        np.random.seed(seed)
+        ref = np.stack([np.random.permutation(n) for _ in range(rep)])
+        np.random.seed(seed)
+        rows = torch.empty((rep, n), dtype=torch.int32)
+        with NumpyGlobalPermutationJob(rows, rep) as job:
+            job.wait(rep - 1)
+        return np.array_equal(rows.numpy(), ref)
+
+    for k in range(25):
+        assert check(k, 3000 + 17 * k, 1 + k % 7), k
+    # two jobs interleaved: different generator states, each written to its own rows
+    np.random.seed(1)
+    s1 = np.random.get_state()
+    ref1 = np.stack([np.random.permutation(5000) for _ in range(3)])
+    np.random.seed(2)
+    ref2 = np.stack([np.random.permutation(7000) for _ in range(4)])
+    r1, r2 = torch.empty((3, 5000), dtype=torch.int32), torch.empty((4, 7000), dtype=torch.int32)
+    np.random.set_state(s1)
+    j1 = NumpyGlobalPermutationJob(r1, 3)
+    np.random.seed(2)
+    j2 = NumpyGlobalPermutationJob(r2, 4)
+    j2.wait(3); j1.wait(2)
+    j2.__exit__(None, None, None)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")            # job 1 finds the global stream moved by job 2: reported, not an error
+        j1.__exit__(None, None, None)
+    assert np.array_equal(r1.numpy(), ref1) and np.array_equal(r2.numpy(), ref2)
+    pid = os.fork()
+    if pid == 0:                                   # child: no parked threads survived the fork
+        ok = False
+        try:
+            ok = check(77, 4096, 3)
+        finally:
+            os._exit(0 if ok else 1)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
 def test_vector_buffer_add_slice_path_equals_fancy_path():
     """Lock-step adds (ids = arange) take the strided-slice write; any other id order takes the fancy-indexed write.
     Same buffer contents, same returned (index, ep_return, ep_len, ep_start) rows (manager.py:131-198)."""
