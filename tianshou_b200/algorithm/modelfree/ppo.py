@@ -107,18 +107,28 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         return (self.rollout_partition == "shared" and self._ranks()[1] > 1 and dist.is_available() and dist.is_initialized()
                 and dist.get_backend() == "nccl")
 
+    @staticmethod
+    def _pack_numpy_state(st: tuple) -> np.ndarray:
+        """numpy's legacy MT19937 state tuple as 627 float64 (every field is exactly representable: 32-bit words, small ints)."""
+        out = np.empty(627, dtype=np.float64)
+        out[:624] = np.asarray(st[1], dtype=np.float64)
+        out[624], out[625], out[626] = float(st[2]), float(st[3]), float(st[4])
+        return out
+
+    @staticmethod
+    def _unpack_numpy_state(kind: str, h: np.ndarray) -> tuple:
+        return (kind, h[:624].astype(np.uint32), int(h[624]), int(h[625]), float(h[626]))
+
     def _broadcast_numpy_state(self) -> None:
         """numpy's global legacy state of rank 0 -> every rank (they all consumed the same draws: rank 0 made them)."""
         import torch.distributed as dist
         st = np.random.get_state()
         t = torch.zeros(627, dtype=torch.float64, device=self.device)
         if dist.get_rank() == 0:
-            t[:624] = torch.from_numpy(np.asarray(st[1], dtype=np.float64)).to(self.device)
-            t[624], t[625], t[626] = float(st[2]), float(st[3]), float(st[4])
+            t.copy_(torch.from_numpy(self._pack_numpy_state(st)))
         dist.broadcast(t, 0)
         if dist.get_rank() != 0:
-            h = t.cpu().numpy()
-            np.random.set_state((st[0], h[:624].astype(np.uint32), int(h[624]), int(h[625]), float(h[626])))
+            np.random.set_state(self._unpack_numpy_state(st[0], t.cpu().numpy()))
 
     def _one_pass(self, batch: Batch, perm_r: torch.Tensor, bounds: list[tuple[int, int]], hp: Any, stats: torch.Tensor,
                   r: int, rank: int, wsize: int) -> None:
