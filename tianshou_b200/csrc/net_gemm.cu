@@ -211,20 +211,33 @@ __global__ void __launch_bounds__(kThreads, 1) net_gemm_kernel(const GemmParams 
             for (int j = 0; j < 16; ++j) v[j] = 0.0f;
         }
         if (m < P.M) {
+            float* row = cbase + (int64_t)m * ldc + n0 + c0;
+            if (!plain) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c0 + j;
-                if (n < P.N) {
-                    float x = v[j];
-                    float* dst = cbase + (int64_t)m * ldc + n;
-                    if (!plain) {
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < P.N) {
+                        float x = v[j];
                         if (P.bias) x += __ldg(P.bias + n);
                         x = apply_act(x, P.act);
                         if (P.mask) x = apply_act_grad(x, __ldg(P.mask + (int64_t)m * P.ld_mask + n), P.mask_kind);
-                        if (P.accumulate) x += *dst;
+                        if (P.accumulate) x += row[j];
+                        v[j] = x;
                     }
-                    *dst = x;
                 }
+            }
+            // a lane owns 16 consecutive columns of ITS row: four 16-byte stores when the run is whole and aligned (a scalar
+            // store per element makes every warp store touch 32 sectors -- ~8 us for a 128 x 128 tile, profiles/r2d_net_gemm_ncu.md)
+            if (n0 + c0 + 16 <= P.N && (reinterpret_cast<uintptr_t>(row) & 15u) == 0) {
+                float4* r4 = reinterpret_cast<float4*>(row);
+                r4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                r4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                r4[2] = make_float4(v[8], v[9], v[10], v[11]);
+                r4[3] = make_float4(v[12], v[13], v[14], v[15]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + c0 + j < P.N) row[j] = v[j];
             }
         }
     }
