@@ -93,13 +93,15 @@ class FusedActorCriticUpdate(ActorCriticOnPolicyAlgorithm):
         if wanted and (not remote or self._ranks()[0] == 0):
             job = NumpyGlobalPermutationJob(self._host_perm_rows(repeat, len(buffer)), repeat)
         self._perm_job = job if not (remote and job is None) else "rank0"
+        completed = False
         try:
             yield job
+            completed = True
         finally:
             self._perm_job = None
             if job is not None:
                 job.__exit__(None, None, None)      # joins the threads, writes the advanced state back into numpy
-            if remote:
+            if remote and completed:                # (not while an exception unwinds: the other ranks may never reach the collective)
                 self._broadcast_numpy_state()
 
     def _shared_order_from_rank0(self) -> bool:
