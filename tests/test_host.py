@@ -297,6 +297,40 @@ def test_numpy_state_pack_roundtrip():
     assert np.array_equal(np.random.standard_normal(1), g1)       # the cached gaussian survived
 
 
+def test_numpy_permutation_job_numa_confinement(tmp_path):
+    """The crew is confined to the CPUs of the caller's NUMA node (csrc/hostperm.cu caller_node_cpus).  Fake two-node topology
+    through TS_B200_SYSFS_NODE_DIR: the job reports the confinement and still reproduces numpy's stream."""
+    import subprocess
+    import sys
+    cpus = sorted(os.sched_getaffinity(0))
+    if len(cpus) < 4:
+        pytest.skip("needs >= 4 CPUs")
+    half = len(cpus) // 2
+    for k, part in enumerate((cpus[:half], cpus[half:])):
+        d = tmp_path / f"node{k}"
+        d.mkdir()
+        (d / "cpulist").write_text(",".join(str(c) for c in part) + "\n")
+    code = (
+        "import numpy as np, torch\n"
+        "from tianshou_b200.data.batch import NumpyGlobalPermutationJob\n"
+        "np.random.seed(3); ref = np.stack([np.random.permutation(70001) for _ in range(4)])\n"
+        "np.random.seed(3); rows = torch.empty((4, 70001), dtype=torch.int32)\n"
+        "with NumpyGlobalPermutationJob(rows, 4) as job:\n"
+        "    job.wait(3)\n"
+        "assert np.array_equal(rows.numpy(), ref)\n"
+        "print('rows ok')\n")
+    env = dict(os.environ, TS_B200_SYSFS_NODE_DIR=str(tmp_path), TS_B200_PERM_PIN_MIN_CPUS="2", TS_B200_PERM_TRACE="1",
+               PYTHONPATH=os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    env.pop("TS_B200_PERM_PIN", None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "rows ok" in r.stdout, r.stderr[-2000:]
+    m = re.search(r"numa_pinned=(\d) \((\d+) cpus\)", r.stderr)
+    assert m and m.group(1) == "1" and int(m.group(2)) in (half, len(cpus) - half), r.stderr[-500:]
+    env["TS_B200_PERM_PIN"] = "0"
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "numa_pinned=0" in r.stderr
+
+
 def test_vector_buffer_add_slice_path_equals_fancy_path():
     """Lock-step adds (ids = arange) take the strided-slice write; any other id order takes the fancy-indexed write.
     Same buffer contents, same returned (index, ep_return, ep_len, ep_start) rows (manager.py:131-198)."""

@@ -109,30 +109,44 @@ inline bool parse_cpulist(const char* s, cpu_set_t* out) {
     }
     return any;
 }
+// The machine's NUMA nodes, read from sysfs ONCE per process (a job is started at the top of every update()).
+inline const std::vector<cpu_set_t>& numa_nodes() {
+    static std::vector<cpu_set_t> nodes;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* base = std::getenv("TS_B200_SYSFS_NODE_DIR");          // tests point this at a fake topology
+        if (base == nullptr || std::strlen(base) > 160) base = "/sys/devices/system/node";
+        for (int node = 0; node < 64; ++node) {
+            char path[256];
+            std::snprintf(path, sizeof(path), "%s/node%d/cpulist", base, node);
+            FILE* f = std::fopen(path, "r");
+            if (f == nullptr) continue;
+            char buf[4096];
+            cpu_set_t cpus;
+            if (std::fgets(buf, sizeof(buf), f) != nullptr && parse_cpulist(buf, &cpus)) nodes.push_back(cpus);
+            std::fclose(f);
+        }
+    });
+    return nodes;
+}
 inline NodeCpus caller_node_cpus() {
     NodeCpus r;
     const char* env = std::getenv("TS_B200_PERM_PIN");
     if (env != nullptr && env[0] == '0') return r;
+    const std::vector<cpu_set_t>& nodes = numa_nodes();
+    if (nodes.size() < 2) return r;           // one node: nothing to choose
     const int cpu = sched_getcpu();
-    if (cpu < 0) return r;
     cpu_set_t allowed;
-    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return r;
-    int nodes_seen = 0;
-    for (int node = 0; node < 64; ++node) {
-        char path[96];
-        std::snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
-        FILE* f = std::fopen(path, "r");
-        if (f == nullptr) continue;
-        ++nodes_seen;
-        char buf[4096];
+    if (cpu < 0 || sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return r;
+    for (const cpu_set_t& node : nodes) {
+        if (!CPU_ISSET(cpu, &node)) continue;
         cpu_set_t cpus;
-        const bool ok = std::fgets(buf, sizeof(buf), f) != nullptr && parse_cpulist(buf, &cpus);
-        std::fclose(f);
-        if (!ok || !CPU_ISSET(cpu, &cpus) || r.valid) continue;
-        CPU_AND(&cpus, &cpus, &allowed);
-        if (CPU_COUNT(&cpus) >= 8) { r.valid = true; r.set = cpus; }
+        CPU_AND(&cpus, &node, &allowed);
+        const char* min_env = std::getenv("TS_B200_PERM_PIN_MIN_CPUS");
+        const int min_cpus = min_env != nullptr ? std::atoi(min_env) : 8;
+        if (CPU_COUNT(&cpus) >= min_cpus) { r.valid = true; r.set = cpus; }
+        break;
     }
-    if (nodes_seen < 2) r.valid = false;      // one node: nothing to choose
     return r;
 }
 
