@@ -375,7 +375,9 @@ int ts_host_perm_job_start(const uint32_t* key, int32_t pos, int64_t n, int32_t 
 int ts_host_perm_job_wait(void* job, int32_t r);
 int ts_host_perm_job_finish(void* job, uint32_t* key_out, int32_t* pos_out);
 
-/* Asynchronous feed of a job's rows to the device (replaces the per-pass `perm.to(device)` of a host-driven loop): for
+/* Asynchronous feed of a job's rows to the device -- the hand-over of `Batch.split`'s per-pass index array
+ * (tianshou/data/batch.py:1209-1215: `indices = np.random.permutation(length)`, then one slice per minibatch) to the update
+ * kernels; replaces the per-pass `perm.to(device)` of a host-driven loop: for
  * r in [0, repeat) a host function on an internal copy stream blocks that stream until row r is complete, then
  * host_rows[r] (pinned, the job's `out`) is copied to dev_rows[r] and an event is recorded.  ts_host_perm_feed_wait_row
  * makes `stream` wait for row r (ts_ppo_update does it before pass r when given the feed), so one asynchronous call enqueues
